@@ -1,0 +1,162 @@
+/*
+ * adas_b200.h -- C ABI of libadas_b200.so: the B200-native (sm_100a) replacement for the
+ * ONNXRuntime / TensorRT dispatch behind the reference's coreEngine.py, plus the fused
+ * per-frame post-processing (YOLO decode + NMS, UFLDv2 row/col-anchor decode, ByteTrack
+ * IoU cost + linear assignment).
+ *
+ * Conventions
+ *   - every entry point returns an int status: 0 = ok, non-zero = error; the message is
+ *     available (thread-local) through adas_last_error().
+ *   - plain pointers and sizes only; no torch / numpy types.  "host" pointers are ordinary
+ *     (pageable or pinned) CPU memory, "dev" pointers are CUDA device memory on the handle's
+ *     device (e.g. a torch CUDA tensor's data_ptr()).
+ *   - a handle owns one device + one private CUDA stream; calls on one handle are serialised
+ *     and synchronous (results are on the host / complete on return) unless the function name
+ *     ends in _async.  This mirrors TensorRTBase.inference (reference coreEngine.py:93-118:
+ *     H2D memcpy -> execute -> D2H memcpy -> stream.synchronize()).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repo root).
+ */
+#ifndef ADAS_B200_H
+#define ADAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct adas_engine adas_engine;   /* opaque: one plan (network) on one device */
+
+/* model kinds stored in the plan header */
+enum { ADAS_MODEL_YOLOV8 = 0, ADAS_MODEL_YOLOV5 = 1, ADAS_MODEL_UFLDV2 = 2 };
+
+/* ---- errors ------------------------------------------------------------------------- */
+/* replaces: Python `raise Exception(...)` in coreEngine.py:12-14,20,26 */
+const char* adas_last_error(void);
+int         adas_version(void);
+/* number of CUDA kernels launched by this library in this process (all handles) */
+int64_t     adas_launch_count(void);
+
+/* ---- engine lifecycle ------------------------------------------------------------------
+ * replaces: TensorRTEngine.__init__ / OnnxEngine.__init__ (coreEngine.py:122-142,161-170):
+ * deserialize a plan file (.b200w, produced by the packer), allocate device buffers for
+ * batches up to max_batch, create the stream.  `device` replaces the hard-coded
+ * cuda.Device(0) (coreEngine.py:47).  conv_impl: 0 = tcgen05 implicit-GEMM (product path),
+ * 1 = plain SIMT CUDA-core kernel (validation path for tests; same plan, same buffers). */
+int adas_engine_create(const char* plan_path, int device, int max_batch, int conv_impl,
+                       adas_engine** out);
+int adas_engine_destroy(adas_engine* e);
+
+/* replaces: get_engine_input_shape / get_engine_output_shape (coreEngine.py:144-148,178-182).
+ * in_shape4 = [N(=1), C, H, W].  out_shapes: n_out rows of 4 int64 (unused dims = 0),
+ * out_ranks[n_out].  Shapes are per batch-1 like the reference bindings. */
+int adas_engine_model_kind(const adas_engine* e, int* kind);
+int adas_engine_input_shape(const adas_engine* e, int64_t in_shape4[4]);
+int adas_engine_num_outputs(const adas_engine* e, int* n_out);
+int adas_engine_output_shape(const adas_engine* e, int idx, int64_t shape4[4], int* rank);
+
+/* replaces: engine_inference(input_tensor) (coreEngine.py:150-157,184-186).
+ * input: fp32 NCHW [batch,C,H,W] on the HOST; outs[i]: HOST fp32 buffers the caller
+ * allocated with batch * prod(shape_i[1:]) elements.  H2D, the network, the head decode
+ * (YOLOv8: DFL+dist2bbox+sigmoid -> [batch,84,8400]; YOLOv5: sigmoid/grid/anchor ->
+ * [batch,25200,85]; UFLDv2: the 4 head tensors) and D2H all happen inside the call. */
+int adas_engine_infer(adas_engine* e, const float* input_nchw_host, int batch,
+                      float* const* outs_host);
+/* same, but input and outputs are DEVICE pointers (no PCIe traffic; used by bench `value`) */
+int adas_engine_infer_dev(adas_engine* e, const float* input_nchw_dev, int batch,
+                          float* const* outs_dev);
+
+/* ---- fused YOLO detect ------------------------------------------------------------------
+ * replaces YoloDetector.DetectFrame up to (not including) RectInfo construction
+ * (ObjectDetector/yoloDetector.py:96-168, ObjectDetector/utils.py:42-87,161-256):
+ * letterbox (cv2-exact fixed-point bilinear, pad 114) + BGR->RGB/255 + network + head decode
+ * + per-anchor argmax / strict score threshold / ordered compaction + box un-letterboxing
+ * + the reference's class-agnostic "soft" NMS (hard suppression, +1 area convention,
+ * duplicate-emitting swap) -- all on the device.
+ *   frames: batch x H x W x 3 uint8 BGR (host or device per `frames_on_device`)
+ *   outputs (host): for frame b, count[b] kept detections in NMS emission order;
+ *     boxes_xywh[b*max_det*4 ...] float32 (x,y,w,h in source-image pixels),
+ *     scores[b*max_det ...] float32, class_ids[b*max_det ...] int32,
+ *     cand_index[b*max_det ...] int32 = index into the pre-NMS candidate list (may repeat).
+ *   n_candidates[b] (optional, may be NULL): number of pre-NMS candidates.
+ * box_score / nms_iou are doubles because the reference compares float32 scores against the
+ * Python-float (float64) thresholds (yoloDetector.py:128, utils.py:249). */
+int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device, int batch,
+                     int H, int W, double box_score, double nms_iou, int max_det,
+                     float* boxes_xywh, float* scores, int32_t* class_ids,
+                     int32_t* cand_index, int32_t* counts, int32_t* n_candidates);
+
+/* post-processing only, from a raw head tensor already on the host (parity tests for
+ * rows E,F,N of SURVEY 8a without the network): raw is [batch,84,A] (kind YOLOv8, channel
+ * major) or [batch,A,5+nc] (kind YOLOv5).  Letterbox geometry as Scaler would record it. */
+int adas_yolo_postprocess(int device, const float* raw_host, int model_kind, int batch,
+                          int n_anchors, int n_classes, int in_h, int in_w, int src_h, int src_w,
+                          double box_score, double nms_iou, int max_det, float* boxes_xywh,
+                          float* scores, int32_t* class_ids, int32_t* cand_index,
+                          int32_t* counts, int32_t* n_candidates);
+
+/* letterbox pre-processing alone (rows A,B): frames u8 BGR host -> fp32 NCHW host blob */
+int adas_yolo_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W,
+                         int in_h, int in_w, float* blob_nchw_host);
+
+/* ---- fused UFLDv2 lane detect ------------------------------------------------------------
+ * replaces UltrafastLaneDetectorV2.DetectFrame up to lanes_points / lanes_status
+ * (TrafficLaneDetector/ufldDetector/ultrafastLaneDetectorV2.py:96-181).
+ *   outputs (host): pts[b][lane(4)][max_pts(=max(num_cls_row,num_cls_col))][2] int32,
+ *   npts[b][4] int32, status[b][4] uint8; lane order left-side, left-ego, right-ego,
+ *   right-side (ultrafastLaneDetectorV2.py:143-145,181).  coords_f (optional) receives the
+ *   pre-truncation float64 coordinate of the expectation axis for tolerance tests. */
+int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device, int batch,
+                     int H, int W, int32_t* pts, int32_t* npts, uint8_t* status,
+                     double* coords_f);
+
+/* decode only, from the 4 head tensors concatenated per frame ([batch, total_dim] fp32 host,
+ * order loc_row, loc_col, exist_row, exist_col) */
+int adas_ufld_postprocess(int device, const float* heads_host, int batch, int num_grid_row,
+                          int num_cls_row, int num_grid_col, int num_cls_col, int num_lanes,
+                          int img_w, int img_h, const double* row_anchor,
+                          const double* col_anchor, int32_t* pts, int32_t* npts,
+                          uint8_t* status, double* coords_f);
+
+/* UFLD pre-processing alone (row H): u8 BGR host -> fp32 NCHW host [batch,3,in_h,in_w] */
+int adas_ufld_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W,
+                         int in_h, int in_w, double crop_ratio, float* blob_nchw_host);
+
+/* ---- ByteTrack association kernels -------------------------------------------------------
+ * adas_iou_cost replaces matching.iou_distance (+ optional fuse_score)
+ * (ObjectTracker/byteTrack/matching.py:34-80,108-116): cost[t*D+d] = 1 - iou(a_t, b_d)
+ * (no +1 convention), fused: 1 - iou * det_score[d].  float64 in/out, host pointers.
+ * `problems` independent (T_i x D_i) problems are batched: offsets arrays have
+ * problems+1 entries (box offsets in units of boxes; cost offsets in elements). */
+int adas_iou_cost(int device, int problems, const double* a_tlbr, const int32_t* a_off,
+                  const double* b_tlbr, const int32_t* b_off, const double* det_scores,
+                  int fuse, double* cost, const int64_t* cost_off);
+
+/* adas_lap replaces matching.linear_assignment -> lap.lapjv(cost, extend_cost=True,
+ * cost_limit=thresh) (matching.py:20-31): exact minimum of
+ *   sum(cost[matched]) + thresh/2 * (#unmatched rows + #unmatched cols).
+ * x[t] = matched column or -1, y[d] = matched row or -1. One warp per problem. */
+int adas_lap(int device, int problems, const double* cost, const int64_t* cost_off,
+             const int32_t* T, const int32_t* D, const double* thresh, int32_t* x,
+             const int32_t* x_off, int32_t* y, const int32_t* y_off);
+
+/* adas_associate: one association stage of BYTETracker.update in a single call -- replaces the sequence
+ * iou_distance -> [fuse_score] -> linear_assignment (ObjectTracker/byteTrack/byteTracker.py:105-108,129-130,
+ * 149-152).  a_tlbr [T,4], b_tlbr [D,4], det_scores [D] (used when fuse != 0), float64 host pointers.
+ * Outputs: x[T], y[D] as adas_lap; cost_out (optional, may be NULL) receives the T*D cost matrix. */
+int adas_associate(int device, int T, int D, const double* a_tlbr, const double* b_tlbr,
+                   const double* det_scores, int fuse, double thresh, int32_t* x, int32_t* y,
+                   double* cost_out);
+
+/* ---- optional multi-GPU gather -------------------------------------------------------------
+ * (no reference counterpart: the reference is single-GPU)  The gather of
+ * fixed-size detection records across ranks is done with torch.distributed (NCCL) in the
+ * Python host layer; the library only needs to expose its stream for ordering. */
+int adas_engine_stream(const adas_engine* e, void** cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAS_B200_H */

@@ -1,0 +1,1 @@
+from .byteTrack.byteTracker import BYTETracker

@@ -1,0 +1,245 @@
+"""_capi.py -- ctypes binding of libadas_b200.so (the C ABI declared in include/adas_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or there is no sm_100
+device, the calls raise.  Errors returned by the library become Python `Exception`s, mirroring
+the reference's error style (coreEngine.py:12-14,20,26).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadas_b200.so")
+
+_lib = None
+
+# every symbol include/adas_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "adas_last_error", "adas_version", "adas_launch_count", "adas_engine_create", "adas_engine_destroy",
+    "adas_engine_model_kind", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
+    "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
+    "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
+    "adas_engine_stream",
+]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise Exception(
+                f"libadas_b200.so not built ({LIB_PATH}); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the B200 path.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.adas_last_error.restype = C.c_char_p
+        _lib.adas_launch_count.restype = C.c_int64
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Exception(lib().adas_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().adas_launch_count())
+
+
+def _p(a: np.ndarray, typ):
+    return a.ctypes.data_as(C.POINTER(typ))
+
+
+def as_c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    """Owns one adas_engine handle (one plan on one device with one private stream)."""
+
+    def __init__(self, plan_path: str, device: int = 0, max_batch: int = 1, conv_impl: int = 0):
+        self._h = C.c_void_p()
+        check(lib().adas_engine_create(plan_path.encode(), int(device), int(max_batch), int(conv_impl), C.byref(self._h)))
+        self.device, self.max_batch = device, max_batch
+        k = C.c_int()
+        check(lib().adas_engine_model_kind(self._h, C.byref(k)))
+        self.model_kind = k.value
+        s = (C.c_int64 * 4)()
+        check(lib().adas_engine_input_shape(self._h, s))
+        self.input_shape = [int(v) for v in s]
+        n = C.c_int()
+        check(lib().adas_engine_num_outputs(self._h, C.byref(n)))
+        self.output_shapes = []
+        for i in range(n.value):
+            r = C.c_int()
+            check(lib().adas_engine_output_shape(self._h, i, s, C.byref(r)))
+            self.output_shapes.append([int(v) for v in s][: r.value])
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().adas_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # engine_inference: fp32 NCHW host -> list of fp32 host arrays
+    def infer(self, x: np.ndarray):
+        x = as_c(x, np.float32)
+        batch = int(x.shape[0])
+        outs = [np.empty([batch] + s[1:], np.float32) for s in self.output_shapes]
+        arr = (C.POINTER(C.c_float) * len(outs))(*[_p(o, C.c_float) for o in outs])
+        check(lib().adas_engine_infer(self._h, _p(x, C.c_float), batch, arr))
+        return outs
+
+    def infer_dev(self, x_ptr: int, batch: int, out_ptrs):
+        arr = (C.POINTER(C.c_float) * len(out_ptrs))(*[C.cast(C.c_void_p(p), C.POINTER(C.c_float)) for p in out_ptrs])
+        check(lib().adas_engine_infer_dev(self._h, C.cast(C.c_void_p(x_ptr), C.POINTER(C.c_float)), batch, arr))
+
+    def yolo_detect(self, frames, box_score: float, nms_iou: float, max_det: int = 300, on_device: bool = False, shape=None):
+        """frames: uint8 [B,H,W,3] numpy (host) or (device pointer, (B,H,W)) when on_device."""
+        if on_device:
+            ptr, (B, H, W) = frames, shape
+            fptr = C.cast(C.c_void_p(ptr), C.POINTER(C.c_uint8))
+        else:
+            frames = as_c(frames, np.uint8)
+            B, H, W = frames.shape[:3]
+            fptr = _p(frames, C.c_uint8)
+        boxes = np.empty((B, max_det, 4), np.float32)
+        scores = np.empty((B, max_det), np.float32)
+        cls = np.empty((B, max_det), np.int32)
+        idx = np.empty((B, max_det), np.int32)
+        counts = np.empty((B,), np.int32)
+        ncand = np.empty((B,), np.int32)
+        check(lib().adas_yolo_detect(self._h, fptr, 1 if on_device else 0, B, H, W, C.c_double(box_score), C.c_double(nms_iou), max_det,
+                                     _p(boxes, C.c_float), _p(scores, C.c_float), _p(cls, C.c_int32), _p(idx, C.c_int32),
+                                     _p(counts, C.c_int32), _p(ncand, C.c_int32)))
+        return boxes, scores, cls, idx, counts, ncand
+
+    def ufld_detect(self, frames, on_device: bool = False, shape=None, want_coords: bool = False):
+        if on_device:
+            ptr, (B, H, W) = frames, shape
+            fptr = C.cast(C.c_void_p(ptr), C.POINTER(C.c_uint8))
+        else:
+            frames = as_c(frames, np.uint8)
+            B, H, W = frames.shape[:3]
+            fptr = _p(frames, C.c_uint8)
+        mp = max(self.output_shapes[0][2], self.output_shapes[1][2])
+        pts = np.empty((B, 4, mp, 2), np.int32)
+        npts = np.empty((B, 4), np.int32)
+        status = np.empty((B, 4), np.uint8)
+        coords = np.empty((B, 4, mp), np.float64) if want_coords else None
+        check(lib().adas_ufld_detect(self._h, fptr, 1 if on_device else 0, B, H, W, _p(pts, C.c_int32), _p(npts, C.c_int32),
+                                     _p(status, C.c_uint8), _p(coords, C.c_double) if want_coords else None))
+        return pts, npts, status, coords
+
+
+def yolo_postprocess(raw: np.ndarray, model_kind: int, n_classes: int, in_hw, src_hw, box_score: float, nms_iou: float,
+                     max_det: int = 300, device: int = 0):
+    raw = as_c(raw, np.float32)
+    B = raw.shape[0]
+    A = raw.shape[2] if model_kind == 0 else raw.shape[1]
+    boxes = np.empty((B, max_det, 4), np.float32)
+    scores = np.empty((B, max_det), np.float32)
+    cls = np.empty((B, max_det), np.int32)
+    idx = np.empty((B, max_det), np.int32)
+    counts = np.empty((B,), np.int32)
+    ncand = np.empty((B,), np.int32)
+    check(lib().adas_yolo_postprocess(device, _p(raw, C.c_float), model_kind, B, A, n_classes, in_hw[0], in_hw[1], src_hw[0], src_hw[1],
+                                      C.c_double(box_score), C.c_double(nms_iou), max_det, _p(boxes, C.c_float), _p(scores, C.c_float),
+                                      _p(cls, C.c_int32), _p(idx, C.c_int32), _p(counts, C.c_int32), _p(ncand, C.c_int32)))
+    return boxes, scores, cls, idx, counts, ncand
+
+
+def yolo_preprocess(frames: np.ndarray, in_hw, device: int = 0) -> np.ndarray:
+    frames = as_c(frames, np.uint8)
+    B, H, W = frames.shape[:3]
+    blob = np.empty((B, 3, in_hw[0], in_hw[1]), np.float32)
+    check(lib().adas_yolo_preprocess(device, _p(frames, C.c_uint8), B, H, W, in_hw[0], in_hw[1], _p(blob, C.c_float)))
+    return blob
+
+
+def ufld_preprocess(frames: np.ndarray, in_hw, crop_ratio: float, device: int = 0) -> np.ndarray:
+    frames = as_c(frames, np.uint8)
+    B, H, W = frames.shape[:3]
+    blob = np.empty((B, 3, in_hw[0], in_hw[1]), np.float32)
+    check(lib().adas_ufld_preprocess(device, _p(frames, C.c_uint8), B, H, W, in_hw[0], in_hw[1], C.c_double(crop_ratio), _p(blob, C.c_float)))
+    return blob
+
+
+def ufld_postprocess(heads: np.ndarray, dims, img_wh, row_anchor, col_anchor, device: int = 0, want_coords: bool = True):
+    heads = as_c(heads, np.float32)
+    B = heads.shape[0]
+    ngr, ncr, ngc, ncc, nl = dims
+    mp = max(ncr, ncc)
+    pts = np.empty((B, 4, mp, 2), np.int32)
+    npts = np.empty((B, 4), np.int32)
+    status = np.empty((B, 4), np.uint8)
+    coords = np.empty((B, 4, mp), np.float64)
+    ra, ca = as_c(row_anchor, np.float64), as_c(col_anchor, np.float64)
+    check(lib().adas_ufld_postprocess(device, _p(heads, C.c_float), B, ngr, ncr, ngc, ncc, nl, img_wh[0], img_wh[1], _p(ra, C.c_double),
+                                      _p(ca, C.c_double), _p(pts, C.c_int32), _p(npts, C.c_int32), _p(status, C.c_uint8),
+                                      _p(coords, C.c_double)))
+    return pts, npts, status, coords
+
+
+def iou_cost(a_list, b_list, scores_list=None, device: int = 0):
+    """Batched 1 - IoU (optionally fused with detection scores). Lists of [T_i,4] / [D_i,4] float64 tlbr arrays."""
+    P = len(a_list)
+    a_off = np.zeros(P + 1, np.int32)
+    b_off = np.zeros(P + 1, np.int32)
+    c_off = np.zeros(P + 1, np.int64)
+    for i in range(P):
+        a_off[i + 1] = a_off[i] + len(a_list[i])
+        b_off[i + 1] = b_off[i] + len(b_list[i])
+        c_off[i + 1] = c_off[i] + len(a_list[i]) * len(b_list[i])
+    a = as_c(np.concatenate([np.asarray(x, np.float64).reshape(-1, 4) for x in a_list]) if P else np.zeros((0, 4)), np.float64)
+    b = as_c(np.concatenate([np.asarray(x, np.float64).reshape(-1, 4) for x in b_list]) if P else np.zeros((0, 4)), np.float64)
+    fuse = scores_list is not None
+    sc = as_c(np.concatenate([np.asarray(s, np.float64).ravel() for s in scores_list]) if fuse else np.zeros(1), np.float64)
+    cost = np.empty(int(c_off[-1]), np.float64)
+    if cost.size:
+        check(lib().adas_iou_cost(device, P, _p(a, C.c_double), _p(a_off, C.c_int32), _p(b, C.c_double), _p(b_off, C.c_int32),
+                                  _p(sc, C.c_double), 1 if fuse else 0, _p(cost, C.c_double), _p(c_off, C.c_int64)))
+    return [cost[c_off[i]:c_off[i + 1]].reshape(len(a_list[i]), len(b_list[i])) for i in range(P)]
+
+
+def lap(cost_list, thresh_list, device: int = 0):
+    """Batched exact assignment with lap.lapjv(extend_cost=True, cost_limit=thresh) semantics -> [(x_i, y_i)]."""
+    P = len(cost_list)
+    T = np.array([c.shape[0] for c in cost_list], np.int32)
+    D = np.array([c.shape[1] for c in cost_list], np.int32)
+    c_off = np.zeros(P + 1, np.int64)
+    x_off = np.zeros(P + 1, np.int32)
+    y_off = np.zeros(P + 1, np.int32)
+    for i in range(P):
+        c_off[i + 1] = c_off[i] + int(T[i]) * int(D[i])
+        x_off[i + 1] = x_off[i] + T[i]
+        y_off[i + 1] = y_off[i] + D[i]
+    cost = as_c(np.concatenate([np.asarray(c, np.float64).ravel() for c in cost_list]) if P else np.zeros(0), np.float64)
+    th = as_c(thresh_list, np.float64)
+    x = np.full(max(int(x_off[-1]), 1), -1, np.int32)
+    y = np.full(max(int(y_off[-1]), 1), -1, np.int32)
+    check(lib().adas_lap(device, P, _p(cost, C.c_double), _p(c_off, C.c_int64), _p(T, C.c_int32), _p(D, C.c_int32), _p(th, C.c_double),
+                         _p(x, C.c_int32), _p(x_off, C.c_int32), _p(y, C.c_int32), _p(y_off, C.c_int32)))
+    return [(x[x_off[i]:x_off[i + 1]].copy(), y[y_off[i]:y_off[i + 1]].copy()) for i in range(P)]
+
+
+def associate(a_tlbr, b_tlbr, det_scores, thresh: float, device: int = 0, want_cost: bool = False):
+    """One ByteTrack association stage on the device: cost = 1 - IoU (optionally fused with scores) + exact assignment."""
+    a = as_c(np.asarray(a_tlbr, np.float64).reshape(-1, 4), np.float64)
+    b = as_c(np.asarray(b_tlbr, np.float64).reshape(-1, 4), np.float64)
+    T, D = a.shape[0], b.shape[0]
+    x = np.full(max(T, 1), -1, np.int32)
+    y = np.full(max(D, 1), -1, np.int32)
+    fuse = det_scores is not None
+    sc = as_c(det_scores if fuse else np.zeros(1), np.float64)
+    cost = np.empty((T, D), np.float64) if want_cost else None
+    check(lib().adas_associate(device, T, D, _p(a, C.c_double), _p(b, C.c_double), _p(sc, C.c_double), 1 if fuse else 0, C.c_double(thresh),
+                               _p(x, C.c_int32), _p(y, C.c_int32), _p(cost, C.c_double) if want_cost else None))
+    return x[:T], y[:D], cost

@@ -1,0 +1,223 @@
+// elementwise.cu -- HBM-bound glue kernels on the padded-NHWC fp16 layout (16-byte vector accesses,
+// one thread per 8 channels, grids sized in waves of the 148 SMs by the launch helpers).
+// These are the non-GEMM graph nodes that ONNXRuntime/TensorRT execute inside the opaque model
+// behind coreEngine.py:150-157/184-186: strided-conv patch gather (feeds the GEMM), MaxPool
+// (SPPF 5x5 s1, ResNet 3x3 s2), nearest Upsample x2 (+Concat by writing a channel slice),
+// LayerNorm (UFLDv2 fc_norm, exportLib/ultrafastLaneV2/model_culane.py:34) and the NCHW fp32
+// input binding -> NHWC fp16 conversion.
+#include "common.h"
+
+namespace adas {
+
+static inline int grid_for(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---- im2col for strided / large-kernel / thin-channel convs ------------------------------------
+// out row = (b, yo+1, xo+1) in the padded output grid, k = (ky*kw + kx)*Cin + c. Cin % 4 == 0.
+// One thread moves 4 channels (8 bytes) of one tap.
+__global__ void im2col_kernel(const __half* __restrict__ in, int in_ld, int in_coff, int B, int H, int W, int Cin,
+                              int kh, int kw, int stride, int pad, int Ho, int Wo, __half* __restrict__ out, int Kpad) {
+    const int c4 = Cin >> 2;
+    const long long per_row = (long long)kh * kw * c4;
+    const long long total = (long long)B * Ho * Wo * per_row;
+    const int Hp = H + 2, Wp = W + 2, Hop = Ho + 2, Wop = Wo + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % c4);
+        long long t = i / c4;
+        const int kx = (int)(t % kw); t /= kw;
+        const int ky = (int)(t % kh); t /= kh;
+        const int xo = (int)(t % Wo); t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int yi = yo * stride - pad + ky;
+        const int xi = xo * stride - pad + kx;
+        uint2 v = make_uint2(0u, 0u);
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+            const size_t r = ((size_t)b * Hp + (yi + 1)) * Wp + (xi + 1);
+            v = *reinterpret_cast<const uint2*>(in + r * in_ld + in_coff + cg * 4);
+        }
+        const size_t orow = ((size_t)b * Hop + (yo + 1)) * Wop + (xo + 1);
+        *reinterpret_cast<uint2*>(out + orow * Kpad + ((ky * kw + kx) * Cin + cg * 4)) = v;
+    }
+}
+
+int launch_im2col(const __half* in, int in_ld, int in_coff, int B, int H, int W, int Cin, int kh, int kw, int stride,
+                  int pad, int Ho, int Wo, __half* out, int Kpad, cudaStream_t st) {
+    ADAS_CHECK(Cin % 4 == 0 && in_ld % 4 == 0 && in_coff % 4 == 0 && Kpad % 4 == 0, "im2col: channel alignment");
+    const long long total = (long long)B * Ho * Wo * kh * kw * (Cin / 4);
+    int blocks = grid_for(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    im2col_kernel<<<blocks, 256, 0, st>>>(in, in_ld, in_coff, B, H, W, Cin, kh, kw, stride, pad, Ho, Wo, out, Kpad);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- max pooling (window positions outside the image are ignored, like torch's -inf padding) ----
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+    uint4 r;
+    const __half2* x = reinterpret_cast<const __half2*>(&a);
+    const __half2* y = reinterpret_cast<const __half2*>(&b);
+    __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = __hmax2(x[j], y[j]);
+    return r;
+}
+
+__global__ void maxpool_kernel(const __half* __restrict__ in, int in_ld, int B, int H, int W, int C, int k, int s, int p,
+                               __half* __restrict__ out, int out_ld, int Ho, int Wo) {
+    const int c8 = C >> 3;
+    const long long total = (long long)B * Ho * Wo * c8;
+    const int Hp = H + 2, Wp = W + 2, Hop = Ho + 2, Wop = Wo + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % c8);
+        long long t = i / c8;
+        const int xo = (int)(t % Wo); t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const __half ninf = __ushort_as_half((unsigned short)0xFC00);
+        const __half2 n2 = __halves2half2(ninf, ninf);
+        uint4 m;
+        __half2* mm = reinterpret_cast<__half2*>(&m);
+        mm[0] = n2; mm[1] = n2; mm[2] = n2; mm[3] = n2;
+        for (int dy = 0; dy < k; ++dy) {
+            const int yi = yo * s - p + dy;
+            if (yi < 0 || yi >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                const int xi = xo * s - p + dx;
+                if (xi < 0 || xi >= W) continue;
+                const size_t r = ((size_t)b * Hp + (yi + 1)) * Wp + (xi + 1);
+                m = hmax8(m, *reinterpret_cast<const uint4*>(in + r * in_ld + cg * 8));
+            }
+        }
+        const size_t orow = ((size_t)b * Hop + (yo + 1)) * Wop + (xo + 1);
+        *reinterpret_cast<uint4*>(out + orow * out_ld + cg * 8) = m;
+    }
+}
+
+int launch_maxpool(const __half* in, int in_ld, int B, int H, int W, int C, int k, int s, int p, __half* out, int out_ld,
+                   int Ho, int Wo, cudaStream_t st) {
+    ADAS_CHECK(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0, "maxpool: channel alignment");
+    const long long total = (long long)B * Ho * Wo * (C / 8);
+    int blocks = grid_for(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    maxpool_kernel<<<blocks, 256, 0, st>>>(in, in_ld, B, H, W, C, k, s, p, out, out_ld, Ho, Wo);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- nearest upsample x2 into a channel slice of the consumer's concat buffer ---------------------
+__global__ void upsample2x_kernel(const __half* __restrict__ in, int in_ld, int B, int H, int W, int C,
+                                  __half* __restrict__ out, int out_ld) {
+    const int c8 = C >> 3;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long total = (long long)B * Ho * Wo * c8;
+    const int Hp = H + 2, Wp = W + 2, Hop = Ho + 2, Wop = Wo + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % c8);
+        long long t = i / c8;
+        const int xo = (int)(t % Wo); t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const size_t r = ((size_t)b * Hp + (yo / 2 + 1)) * Wp + (xo / 2 + 1);
+        const size_t orow = ((size_t)b * Hop + (yo + 1)) * Wop + (xo + 1);
+        *reinterpret_cast<uint4*>(out + orow * out_ld + cg * 8) = *reinterpret_cast<const uint4*>(in + r * in_ld + cg * 8);
+    }
+}
+
+int launch_upsample2x(const __half* in, int in_ld, int B, int H, int W, int C, __half* out, int out_ld, cudaStream_t st) {
+    ADAS_CHECK(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0, "upsample: channel alignment");
+    const long long total = (long long)B * 4 * H * W * (C / 8);
+    int blocks = grid_for(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    upsample2x_kernel<<<blocks, 256, 0, st>>>(in, in_ld, B, H, W, C, out, out_ld);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- LayerNorm over a feature row (one CTA per row), fp32 statistics ------------------------------
+__global__ void layernorm_kernel(const __half* __restrict__ in, int in_ld, int D, int Dn, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int out_ld) {
+    const int row = blockIdx.x;
+    const __half* x = in + (size_t)row * in_ld;
+    __shared__ float red[2][32];
+    float s = 0.f, ss = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = __half2float(x[i]);
+        s += v;
+        ss += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = s; red[1][w] = ss; }
+    __syncthreads();
+    if (w == 0) {
+        s = (l < (int)(blockDim.x >> 5)) ? red[0][l] : 0.f;
+        ss = (l < (int)(blockDim.x >> 5)) ? red[1][l] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (l == 0) { red[0][0] = s; red[1][0] = ss; }
+    }
+    __syncthreads();
+    const float mean = red[0][0] / Dn;
+    const float var = fmaxf(red[1][0] / Dn - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = (__half2float(x[i]) - mean) * rstd * gamma[i] + beta[i];
+        out[(size_t)row * out_ld + i] = __float2half_rn(v);
+    }
+}
+
+int launch_layernorm(const __half* in, int in_ld, int rows, int d_len, int d_norm, const float* gamma, const float* beta,
+                     float eps, __half* out, int out_ld, cudaStream_t st) {
+    layernorm_kernel<<<rows, 256, 0, st>>>(in, in_ld, d_len, d_norm, gamma, beta, eps, out, out_ld);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- fp32 NCHW input binding -> fp16 padded NHWC (C padded to out_ld, extra channels zero) ------------
+__global__ void nchw_to_padded_kernel(const float* __restrict__ in, int B, int C, int H, int W, __half* __restrict__ out,
+                                      int out_ld) {
+    const long long total = (long long)B * H * W;
+    const int Hp = H + 2, Wp = W + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long t = i / W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        const size_t orow = ((size_t)b * Hp + (y + 1)) * Wp + (x + 1);
+        for (int c = 0; c < out_ld; ++c) {
+            float v = 0.f;
+            if (c < C) v = in[(((size_t)b * C + c) * H + y) * W + x];
+            out[orow * out_ld + c] = __float2half_rn(v);
+        }
+    }
+}
+
+int launch_nchw_to_padded(const float* in, int B, int C, int H, int W, __half* out, int out_ld, cudaStream_t st) {
+    const long long total = (long long)B * H * W;
+    int blocks = grid_for(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    nchw_to_padded_kernel<<<blocks, 256, 0, st>>>(in, B, C, H, W, out, out_ld);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_zero_rows(__half* buf, int ld, int C, int row0, int nrows, cudaStream_t st) {
+    ADAS_CUDA(cudaMemset2DAsync(buf + (size_t)row0 * ld, (size_t)ld * 2, 0, (size_t)C * 2, nrows, st));
+    return 0;
+}
+
+}  // namespace adas

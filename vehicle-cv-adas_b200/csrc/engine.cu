@@ -1,0 +1,712 @@
+// engine.cu -- plan loader, per-batch launch programs, CUDA-graph replay and the C ABI (include/adas_b200.h).
+//
+// Replaces the engine layer of the reference (coreEngine.py): TensorRTBase.__init__/_allocate_buffers (:41-88),
+// TensorRTBase.inference (:93-118), TensorRTEngine/OnnxEngine shape queries (:144-148,178-182) and
+// engine_inference (:150-157,184-186).  One handle = one device + one private stream; every activation
+// tensor of the network owns its own HBM buffer (180 GB: no reuse planning, zero halos stay zero forever).
+#include "common.h"
+#include "plan.h"
+#include "../../include/adas_b200.h"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <memory>
+#include <functional>
+
+namespace adas {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int launch_iou_cost(int problems, const double* a, const int32_t* a_off, const double* b, const int32_t* b_off,
+                    const double* det_scores, int fuse, double* cost, const int64_t* cost_off, cudaStream_t st);
+int launch_lap(int problems, const double* cost, const int64_t* cost_off, const int32_t* T, const int32_t* D,
+               const double* thresh, int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off, double* work_v,
+               double* work_minv, int32_t* work_i, cudaStream_t st);
+int lap_max_cols();
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Program {   // launch list for one batch size
+    std::vector<std::function<int(cudaStream_t)>> steps;
+    cudaGraphExec_t graph = nullptr;
+    int runs = 0;
+};
+
+}  // namespace adas
+
+using namespace adas;
+
+struct adas_engine {
+    int device = 0;
+    int max_batch = 1;
+    int conv_impl = 0;
+    bool use_graph = true;
+    cudaStream_t stream = nullptr;
+    PlanHeader hdr;
+    std::vector<PlanBuffer> bufs;
+    std::vector<PlanOp> ops;
+    std::vector<PlanTensor> tensors;
+    std::vector<PlanOutput> outs;
+    void* d_blob = nullptr;
+    std::vector<DevBuf> dbufs;
+    std::map<int, Program> programs;
+    // staging
+    float* d_input = nullptr;        // [max_batch, C, H, W] fp32
+    uint8_t* d_frames = nullptr;     // [max_batch * frame_bytes]
+    size_t frames_cap = 0;
+    float* d_raw = nullptr;          // decoded head tensor (YOLO) [max_batch, ...]
+    size_t raw_per_img = 0;
+    // yolo post scratch
+    YoloPostBufs yp{};
+    int yp_max_det = 0;
+    // ufld
+    float* d_lut = nullptr;          // 3*256 fp32
+    double* d_row_anchor = nullptr;
+    double* d_col_anchor = nullptr;
+    int32_t* d_pts = nullptr; int32_t* d_npts = nullptr; uint8_t* d_status = nullptr; double* d_coords = nullptr;
+    int ufld_max_pts = 0;
+};
+
+namespace adas {
+
+static size_t elem_size(uint32_t dtype) { return dtype == 1 ? 4 : 2; }
+
+static const void* tensor_ptr(const adas_engine* e, int idx) {
+    if (idx < 0) return nullptr;
+    return static_cast<const uint8_t*>(e->d_blob) + e->tensors[idx].offset;
+}
+
+static int build_program(adas_engine* e, int batch, Program* prog) {
+    for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+        const PlanOp& op = e->ops[oi];
+        const int32_t* p = op.p;
+        switch (op.type) {
+            case OP_GEMM: {
+                const int a_buf = p[0], a_coff = p[1], Kc = p[2], ntaps = p[3], w_t = p[4], bias_t = p[5], N = p[6], act = p[7];
+                const int res_buf = p[8], res_coff = p[9], res_pre = p[10], out_buf = p[11], out_coff = p[12], masked = p[13];
+                const int transposed = p[14];
+                int BN = p[15];
+                const PlanBuffer& ab = e->bufs[a_buf];
+                const PlanBuffer& ob = e->bufs[out_buf];
+                ADAS_CHECK(ab.dtype == 0, "op %zu: GEMM input buffer must be fp16", oi);
+                ADAS_CHECK(Kc % 8 == 0 && a_coff % 8 == 0 && ab.C % 8 == 0, "op %zu: K alignment", oi);
+                ADAS_CHECK(ntaps == 1 || (ntaps == 9 && Kc % 64 == 0 && ab.W > 0), "op %zu: tap mode needs Cin %% 64 == 0", oi);
+                GemmParams g;
+                memset(&g, 0, sizeof(g));
+                const int Ktot = ntaps * Kc;
+                const __half* wptr = static_cast<const __half*>(tensor_ptr(e, w_t));
+                ADAS_CHECK((size_t)e->tensors[w_t].bytes >= (size_t)(transposed ? N : N) * Ktot * 2, "op %zu: weight tensor too small", oi);
+                const __half* aptr = static_cast<const __half*>(e->dbufs[a_buf].ptr) + a_coff;
+                const int a_rows = batch * (int)ab.rows_per_img;
+                CUtensorMap tmA, tmB;
+                if (!transposed) {
+                    g.M = a_rows;
+                    g.N = N;
+                    if (BN <= 0) {
+                        // widest tile that divides the work evenly: fewer, fatter CTAs keep smem traffic per MMA low
+                        if (N <= 256) BN = (N + 15) / 16 * 16;
+                        else if (N % 256 == 0) BN = 256;
+                        else if (N % 160 == 0) BN = 160;
+                        else if (N % 128 == 0) BN = 128;
+                        else BN = 256;
+                    }
+                    if (make_tmap_2d(&tmA, aptr, (uint64_t)Kc, (uint64_t)a_rows, (uint64_t)ab.C * 2, 64, 128)) return 1;
+                    if (make_tmap_2d(&tmB, wptr, (uint64_t)Ktot, (uint64_t)N, (uint64_t)Ktot * 2, 64, (uint32_t)BN)) return 1;
+                    g.A = aptr; g.a_ld = (int)ab.C; g.Wt = wptr; g.w_ld = Ktot;
+                    g.out_ld = (int)ob.C;
+                    ADAS_CHECK((int)ob.rows_per_img == (int)ab.rows_per_img, "op %zu: GEMM in/out row geometry differs", oi);
+                } else {
+                    // swap-AB: rows = output features (weights stream once through the A operand), cols = batch rows
+                    g.M = N;
+                    g.N = a_rows;
+                    BN = (a_rows + 15) / 16 * 16;
+                    ADAS_CHECK(BN <= 256, "op %zu: transposed GEMM supports at most 256 activation rows", oi);
+                    if (make_tmap_2d(&tmA, wptr, (uint64_t)Ktot, (uint64_t)N, (uint64_t)Ktot * 2, 64, 128)) return 1;
+                    if (make_tmap_2d(&tmB, aptr, (uint64_t)Kc, (uint64_t)a_rows, (uint64_t)ab.C * 2, 64, (uint32_t)BN)) return 1;
+                    g.A = wptr; g.a_ld = Ktot; g.Wt = aptr; g.w_ld = (int)ab.C;
+                    g.out_ld = (int)ob.C;
+                }
+                g.Kc = Kc; g.ntaps = ntaps; g.Wp = (int)ab.W + 2; g.kpt = (Kc + 63) / 64; g.BN = BN;
+                g.stages = gemm_tc_pick_stages(BN, ntaps * g.kpt);
+                g.act = act; g.out_f32 = ob.dtype == 1 ? 1 : 0;
+                g.transposed = transposed;
+                g.bias = static_cast<const float*>(tensor_ptr(e, bias_t));
+                if (res_buf >= 0) {
+                    const PlanBuffer& rb = e->bufs[res_buf];
+                    g.res = static_cast<const __half*>(e->dbufs[res_buf].ptr) + res_coff;
+                    g.res_ld = res_pre ? -(int)rb.C : (int)rb.C;
+                }
+                g.out = static_cast<uint8_t*>(e->dbufs[out_buf].ptr) + (size_t)out_coff * elem_size(ob.dtype);
+                if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
+                if (e->conv_impl == 0) prog->steps.push_back([tmA, tmB, g](cudaStream_t st) { return gemm_tc_launch(tmA, tmB, g, st); });
+                else prog->steps.push_back([g](cudaStream_t st) { return gemm_simt_launch(g, st); });
+                break;
+            }
+            case OP_IM2COL: {
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[7]];
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr);
+                __half* out = static_cast<__half*>(e->dbufs[p[7]].ptr);
+                const int in_ld = (int)ib.C, in_coff = p[1], H = (int)ib.H, W = (int)ib.W, Cin = p[2], kh = p[3], kw = p[4], s = p[5], pad = p[6];
+                const int Ho = (int)ob.H, Wo = (int)ob.W, Kpad = (int)ob.C;
+                ADAS_CHECK(kh * kw * Cin <= Kpad, "op %zu: im2col K exceeds the patch buffer width", oi);
+                prog->steps.push_back([=](cudaStream_t st) {
+                    return launch_im2col(in, in_ld, in_coff, batch, H, W, Cin, kh, kw, s, pad, Ho, Wo, out, Kpad, st);
+                });
+                break;
+            }
+            case OP_MAXPOOL: {
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[6]];
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr) + p[1];
+                __half* out = static_cast<__half*>(e->dbufs[p[6]].ptr) + p[7];
+                const int in_ld = (int)ib.C, H = (int)ib.H, W = (int)ib.W, C = p[2], k = p[3], s = p[4], pad = p[5];
+                const int out_ld = (int)ob.C, Ho = (int)ob.H, Wo = (int)ob.W;
+                prog->steps.push_back([=](cudaStream_t st) { return launch_maxpool(in, in_ld, batch, H, W, C, k, s, pad, out, out_ld, Ho, Wo, st); });
+                break;
+            }
+            case OP_UPSAMPLE2X: {
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[3]];
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr) + p[1];
+                __half* out = static_cast<__half*>(e->dbufs[p[3]].ptr) + p[4];
+                const int in_ld = (int)ib.C, H = (int)ib.H, W = (int)ib.W, C = p[2], out_ld = (int)ob.C;
+                ADAS_CHECK((int)ob.H == 2 * H && (int)ob.W == 2 * W, "op %zu: upsample geometry", oi);
+                prog->steps.push_back([=](cudaStream_t st) { return launch_upsample2x(in, in_ld, batch, H, W, C, out, out_ld, st); });
+                break;
+            }
+            case OP_LAYERNORM: {
+                // each image's whole slab (rows_per_img * C elements) is one LayerNorm row
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[4]];
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr);
+                __half* out = static_cast<__half*>(e->dbufs[p[4]].ptr);
+                const int in_ld = (int)(ib.rows_per_img * ib.C), d_len = p[1], d_norm = p[5], out_ld = (int)(ob.rows_per_img * ob.C);
+                ADAS_CHECK(d_len <= in_ld && d_len <= out_ld && d_norm > 0, "op %zu: layernorm extent", oi);
+                const float* gamma = static_cast<const float*>(tensor_ptr(e, p[2]));
+                const float* beta = static_cast<const float*>(tensor_ptr(e, p[3]));
+                const float eps = op.f[0];
+                prog->steps.push_back([=](cudaStream_t st) { return launch_layernorm(in, in_ld, batch, d_len, d_norm, gamma, beta, eps, out, out_ld, st); });
+                break;
+            }
+            default:
+                ADAS_CHECK(false, "plan op %zu has unknown type %u", oi, op.type);
+        }
+    }
+    return 0;
+}
+
+// run the network for `batch` images already staged in buffer 0 (fp16 padded NHWC image)
+static int run_plan(adas_engine* e, int batch) {
+    auto it = e->programs.find(batch);
+    if (it == e->programs.end()) {
+        Program prog;
+        if (build_program(e, batch, &prog)) return 1;
+        it = e->programs.emplace(batch, std::move(prog)).first;
+    }
+    Program& pg = it->second;
+    if (pg.graph != nullptr) {
+        ADAS_CUDA(cudaGraphLaunch(pg.graph, e->stream));
+        count_launch((int)pg.steps.size());
+        return 0;
+    }
+    if (e->use_graph && pg.runs >= 1) {
+        // second run: capture the launch list once, replay it from then on
+        cudaGraph_t graph = nullptr;
+        ADAS_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (auto& s : pg.steps) { rc = s(e->stream); if (rc) break; }
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+        ADAS_CUDA(ce);
+        ADAS_CUDA(cudaGraphInstantiate(&pg.graph, graph, 0));
+        ADAS_CUDA(cudaGraphDestroy(graph));
+        ADAS_CUDA(cudaGraphLaunch(pg.graph, e->stream));
+        pg.runs++;
+        return 0;
+    }
+    for (auto& s : pg.steps) if (s(e->stream)) return 1;
+    pg.runs++;
+    return 0;
+}
+
+static int head_decode(adas_engine* e, int batch) {
+    if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) return 0;   // heads are the raw FC output buffer
+    YoloLevel lv[3];
+    ADAS_CHECK(e->outs.size() == 3, "YOLO plan must declare 3 output levels");
+    for (int i = 0; i < 3; ++i) {
+        const PlanOutput& o = e->outs[i];
+        const PlanBuffer& b = e->bufs[o.buffer];
+        lv[i].ptr = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
+        lv[i].ld = (int)b.C; lv[i].H = (int)b.H; lv[i].W = (int)b.W; lv[i].stride = (int)o.stride;
+        lv[i].rows_per_img = (int)b.rows_per_img;
+    }
+    const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
+    if (e->hdr.model_kind == ADAS_MODEL_YOLOV8) return launch_yolov8_head_decode(lv, batch, nc, e->d_raw, A, e->stream);
+    return launch_yolov5_head_decode(lv, batch, nc, e->d_raw, A, e->stream);
+}
+
+static int alloc_yolo_post(YoloPostBufs* w, int B, int A, int max_det) {
+    w->cap = 1024;
+    ADAS_CUDA(cudaMalloc(&w->flags, (size_t)B * A * 4));
+    ADAS_CUDA(cudaMalloc(&w->cls, (size_t)B * A * 4));
+    ADAS_CUDA(cudaMalloc(&w->conf, (size_t)B * A * 4));
+    ADAS_CUDA(cudaMalloc(&w->n_cand, (size_t)B * 4));
+    ADAS_CUDA(cudaMalloc(&w->cand_box, (size_t)B * w->cap * 16));
+    ADAS_CUDA(cudaMalloc(&w->cand_conf, (size_t)B * w->cap * 4));
+    ADAS_CUDA(cudaMalloc(&w->cand_cls, (size_t)B * w->cap * 4));
+    ADAS_CUDA(cudaMalloc(&w->out_box, (size_t)B * max_det * 16));
+    ADAS_CUDA(cudaMalloc(&w->out_score, (size_t)B * max_det * 4));
+    ADAS_CUDA(cudaMalloc(&w->out_cls, (size_t)B * max_det * 4));
+    ADAS_CUDA(cudaMalloc(&w->out_idx, (size_t)B * max_det * 4));
+    ADAS_CUDA(cudaMalloc(&w->out_count, (size_t)B * 4));
+    return 0;
+}
+static void free_yolo_post(YoloPostBufs* w) {
+    cudaFree(w->flags); cudaFree(w->cls); cudaFree(w->conf); cudaFree(w->n_cand); cudaFree(w->cand_box); cudaFree(w->cand_conf);
+    cudaFree(w->cand_cls); cudaFree(w->out_box); cudaFree(w->out_score); cudaFree(w->out_cls); cudaFree(w->out_idx); cudaFree(w->out_count);
+    memset(w, 0, sizeof(*w));
+}
+
+static int copy_yolo_results(const YoloPostBufs& w, int batch, int max_det, float* boxes, float* scores, int32_t* cls, int32_t* idx,
+                             int32_t* counts, int32_t* n_cand, cudaStream_t st) {
+    ADAS_CUDA(cudaMemcpyAsync(boxes, w.out_box, (size_t)batch * max_det * 16, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaMemcpyAsync(scores, w.out_score, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaMemcpyAsync(cls, w.out_cls, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaMemcpyAsync(idx, w.out_idx, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaMemcpyAsync(counts, w.out_count, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> nc(batch);
+    ADAS_CUDA(cudaMemcpyAsync(nc.data(), w.n_cand, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < batch; ++b) {
+        if (n_cand) n_cand[b] = nc[b];
+        ADAS_CHECK(nc[b] <= w.cap, "frame %d: %d candidates exceed the device NMS capacity %d (raise box_score)", b, nc[b], w.cap);
+        if (counts[b] > max_det) counts[b] = max_det;
+    }
+    return 0;
+}
+
+static void ufld_lut_host(float* lut) {
+    // ((float32(v) / 255.0 - mean) / std) evaluated in float64 then cast (ultrafastLaneDetectorV2.py:105-108,112)
+    const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < 256; ++v) lut[c * 256 + v] = (float)((((double)(float)v) / 255.0 - mean[c]) / stdv[c]);
+}
+
+}  // namespace adas
+
+// =====================================================================================================
+//                                            C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* adas_last_error(void) { return adas::g_err; }
+int adas_version(void) { return 100; }
+int64_t adas_launch_count(void) { return (int64_t)adas::g_launches.load(); }
+
+int adas_engine_create(const char* plan_path, int device, int max_batch, int conv_impl, adas_engine** out) {
+    ADAS_CHECK(out != nullptr && plan_path != nullptr, "adas_engine_create: null argument");
+    *out = nullptr;
+    FILE* f = fopen(plan_path, "rb");
+    // same wording class as EngineBase.__init__ (coreEngine.py:12-13)
+    ADAS_CHECK(f != nullptr, "The model path [%s] can't not found!", plan_path);
+    std::unique_ptr<adas_engine> e(new adas_engine());
+    e->device = device; e->max_batch = max_batch; e->conv_impl = conv_impl;
+    const char* ng = getenv("ADAS_B200_NO_GRAPH");
+    e->use_graph = !(ng && ng[0] == '1');
+    bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
+    if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
+    e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);
+    ok = fread(e->bufs.data(), sizeof(PlanBuffer), e->bufs.size(), f) == e->bufs.size() &&
+         fread(e->ops.data(), sizeof(PlanOp), e->ops.size(), f) == e->ops.size() &&
+         fread(e->tensors.data(), sizeof(PlanTensor), e->tensors.size(), f) == e->tensors.size() &&
+         fread(e->outs.data(), sizeof(PlanOutput), e->outs.size(), f) == e->outs.size();
+    if (!ok) { fclose(f); ADAS_CHECK(false, "truncated plan file %s", plan_path); }
+    std::vector<uint8_t> blob(e->hdr.blob_bytes);
+    fseek(f, (long)e->hdr.blob_offset, SEEK_SET);
+    ok = fread(blob.data(), 1, blob.size(), f) == blob.size();
+    fclose(f);
+    ADAS_CHECK(ok, "truncated plan blob in %s", plan_path);
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    ADAS_CHECK(ce == cudaSuccess && ndev > 0, "no CUDA device available: libadas_b200 has no CPU fallback (%s)", cudaGetErrorString(ce));
+    ADAS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ADAS_CUDA(cudaGetDeviceProperties(&prop, device));
+    ADAS_CHECK(prop.major == 10, "device %d is sm_%d%d; libadas_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    ADAS_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    ADAS_CUDA(cudaMalloc(&e->d_blob, blob.size() + 256));
+    ADAS_CUDA(cudaMemcpy(e->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    e->dbufs.resize(e->bufs.size());
+    for (size_t i = 0; i < e->bufs.size(); ++i) {
+        const PlanBuffer& b = e->bufs[i];
+        const size_t bytes = (size_t)max_batch * b.rows_per_img * b.C * elem_size(b.dtype) + 256;
+        ADAS_CUDA(cudaMalloc(&e->dbufs[i].ptr, bytes));
+        ADAS_CUDA(cudaMemset(e->dbufs[i].ptr, 0, bytes));
+        e->dbufs[i].bytes = bytes;
+    }
+    const size_t in_elems = (size_t)e->hdr.in_c * e->hdr.in_h * e->hdr.in_w;
+    ADAS_CUDA(cudaMalloc(&e->d_input, (size_t)max_batch * in_elems * 4));
+    if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) {
+        float lut[768];
+        ufld_lut_host(lut);
+        ADAS_CUDA(cudaMalloc(&e->d_lut, sizeof(lut)));
+        ADAS_CUDA(cudaMemcpy(e->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        const int ncr = (int)e->hdr.meta[1], ncc = (int)e->hdr.meta[3];
+        e->ufld_max_pts = ncr > ncc ? ncr : ncc;
+        // CULane anchors (ModelConfig.init_culane_config, ultrafastLaneDetectorV2.py:47-55): np.linspace semantics
+        std::vector<double> ra(ncr), ca(ncc);
+        // np.linspace(start, stop, n): start + i*step with step = (stop-start)/(n-1), last element forced to stop
+        const double r0 = 0.42, r1 = 1.0, c0 = 0.0, c1 = 1.0;
+        for (int i = 0; i < ncr; ++i) ra[i] = (i == ncr - 1) ? r1 : r0 + (double)i * ((r1 - r0) / (double)(ncr - 1));
+        for (int i = 0; i < ncc; ++i) ca[i] = (i == ncc - 1) ? c1 : c0 + (double)i * ((c1 - c0) / (double)(ncc - 1));
+        ADAS_CUDA(cudaMalloc(&e->d_row_anchor, ncr * 8));
+        ADAS_CUDA(cudaMalloc(&e->d_col_anchor, ncc * 8));
+        ADAS_CUDA(cudaMemcpy(e->d_row_anchor, ra.data(), ncr * 8, cudaMemcpyHostToDevice));
+        ADAS_CUDA(cudaMemcpy(e->d_col_anchor, ca.data(), ncc * 8, cudaMemcpyHostToDevice));
+        ADAS_CUDA(cudaMalloc(&e->d_pts, (size_t)max_batch * 4 * e->ufld_max_pts * 2 * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_npts, (size_t)max_batch * 4 * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_status, (size_t)max_batch * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_coords, (size_t)max_batch * 4 * e->ufld_max_pts * 8));
+    } else {
+        const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
+        e->raw_per_img = e->hdr.model_kind == ADAS_MODEL_YOLOV8 ? (size_t)(4 + nc) * A : (size_t)A * (5 + nc);
+        ADAS_CUDA(cudaMalloc(&e->d_raw, (size_t)max_batch * e->raw_per_img * 4));
+    }
+    *out = e.release();
+    return 0;
+}
+
+int adas_engine_destroy(adas_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& kv : e->programs) if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+    for (auto& b : e->dbufs) cudaFree(b.ptr);
+    cudaFree(e->d_blob); cudaFree(e->d_input); cudaFree(e->d_frames); cudaFree(e->d_raw); cudaFree(e->d_lut);
+    cudaFree(e->d_row_anchor); cudaFree(e->d_col_anchor); cudaFree(e->d_pts); cudaFree(e->d_npts); cudaFree(e->d_status); cudaFree(e->d_coords);
+    if (e->yp.flags) free_yolo_post(&e->yp);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+int adas_engine_model_kind(const adas_engine* e, int* kind) { *kind = (int)e->hdr.model_kind; return 0; }
+int adas_engine_input_shape(const adas_engine* e, int64_t s[4]) {
+    s[0] = 1; s[1] = e->hdr.in_c; s[2] = e->hdr.in_h; s[3] = e->hdr.in_w;
+    return 0;
+}
+int adas_engine_num_outputs(const adas_engine* e, int* n) { *n = e->hdr.model_kind == ADAS_MODEL_UFLDV2 ? 4 : 1; return 0; }
+int adas_engine_output_shape(const adas_engine* e, int idx, int64_t s[4], int* rank) {
+    const uint32_t* m = e->hdr.meta;
+    s[0] = 1; s[1] = s[2] = s[3] = 0;
+    if (e->hdr.model_kind == ADAS_MODEL_YOLOV8) { ADAS_CHECK(idx == 0, "bad output index"); s[1] = 4 + m[0]; s[2] = m[1]; *rank = 3; }
+    else if (e->hdr.model_kind == ADAS_MODEL_YOLOV5) { ADAS_CHECK(idx == 0, "bad output index"); s[1] = m[1]; s[2] = 5 + m[0]; *rank = 3; }
+    else {
+        ADAS_CHECK(idx >= 0 && idx < 4, "bad output index");
+        *rank = 4;
+        if (idx == 0) { s[1] = m[0]; s[2] = m[1]; s[3] = m[4]; }        // loc_row  [ngr, ncr, nl]
+        else if (idx == 1) { s[1] = m[2]; s[2] = m[3]; s[3] = m[4]; }   // loc_col  [ngc, ncc, nl]
+        else if (idx == 2) { s[1] = 2; s[2] = m[1]; s[3] = m[4]; }      // exist_row
+        else { s[1] = 2; s[2] = m[3]; s[3] = m[4]; }                    // exist_col
+    }
+    return 0;
+}
+int adas_engine_stream(const adas_engine* e, void** st) { *st = (void*)e->stream; return 0; }
+
+static int infer_common(adas_engine* e, const float* input, int batch, float* const* outs, bool on_device) {
+    ADAS_CHECK(e != nullptr, "null engine");
+    ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const size_t in_elems = (size_t)e->hdr.in_c * e->hdr.in_h * e->hdr.in_w;
+    const float* din = input;
+    if (!on_device) {
+        ADAS_CUDA(cudaMemcpyAsync(e->d_input, input, (size_t)batch * in_elems * 4, cudaMemcpyHostToDevice, e->stream));
+        din = e->d_input;
+    }
+    const PlanBuffer& ib = e->bufs[0];
+    if (launch_nchw_to_padded(din, batch, (int)e->hdr.in_c, (int)e->hdr.in_h, (int)e->hdr.in_w, static_cast<__half*>(e->dbufs[0].ptr),
+                              (int)ib.C, e->stream)) return 1;
+    if (run_plan(e, batch)) return 1;
+    if (head_decode(e, batch)) return 1;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) {
+        const uint32_t* m = e->hdr.meta;
+        const size_t total = m[5];
+        const size_t sz[4] = {(size_t)m[0] * m[1] * m[4], (size_t)m[2] * m[3] * m[4], (size_t)2 * m[1] * m[4], (size_t)2 * m[3] * m[4]};
+        const PlanOutput& o = e->outs[0];
+        const float* src = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
+        const size_t ld = e->bufs[o.buffer].C;
+        size_t off = 0;
+        for (int k = 0; k < 4; ++k) {
+            ADAS_CUDA(cudaMemcpy2DAsync(outs[k], sz[k] * 4, src + off, ld * 4, sz[k] * 4, batch, kind, e->stream));
+            off += sz[k];
+        }
+        (void)total;
+    } else {
+        ADAS_CUDA(cudaMemcpyAsync(outs[0], e->d_raw, (size_t)batch * e->raw_per_img * 4, kind, e->stream));
+    }
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int adas_engine_infer(adas_engine* e, const float* input, int batch, float* const* outs) { return infer_common(e, input, batch, outs, false); }
+int adas_engine_infer_dev(adas_engine* e, const float* input, int batch, float* const* outs) { return infer_common(e, input, batch, outs, true); }
+
+static int stage_frames(adas_engine* e, const uint8_t* frames, int on_device, int batch, int H, int W, const uint8_t** dptr) {
+    if (on_device) { *dptr = frames; return 0; }
+    const size_t bytes = (size_t)batch * H * W * 3;
+    if (bytes > e->frames_cap) {
+        if (e->d_frames) ADAS_CUDA(cudaFree(e->d_frames));
+        e->d_frames = nullptr;
+        const size_t cap = (size_t)e->max_batch * H * W * 3;
+        ADAS_CUDA(cudaMalloc(&e->d_frames, cap));
+        e->frames_cap = cap;
+    }
+    ADAS_CUDA(cudaMemcpyAsync(e->d_frames, frames, bytes, cudaMemcpyHostToDevice, e->stream));
+    *dptr = e->d_frames;
+    return 0;
+}
+
+int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device, int batch, int H, int W, double box_score,
+                     double nms_iou, int max_det, float* boxes_xywh, float* scores, int32_t* class_ids, int32_t* cand_index,
+                     int32_t* counts, int32_t* n_candidates) {
+    ADAS_CHECK(e != nullptr, "null engine");
+    ADAS_CHECK(e->hdr.model_kind != ADAS_MODEL_UFLDV2, "adas_yolo_detect on a UFLD plan");
+    ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
+    if (e->yp.flags == nullptr || e->yp_max_det != max_det) {
+        if (e->yp.flags) free_yolo_post(&e->yp);
+        if (alloc_yolo_post(&e->yp, e->max_batch, A, max_det)) return 1;
+        e->yp_max_det = max_det;
+    }
+    const uint8_t* dfr = nullptr;
+    if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
+    const LetterboxGeom g = letterbox_geom(H, W, (int)e->hdr.in_h, (int)e->hdr.in_w);
+    if (launch_yolo_pre(dfr, batch, g, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr, e->stream)) return 1;
+    if (run_plan(e, batch)) return 1;
+    if (head_decode(e, batch)) return 1;
+    if (launch_yolo_post(e->d_raw, (int)e->hdr.model_kind, batch, A, nc, g, box_score, nms_iou, max_det, e->yp, e->stream)) return 1;
+    return copy_yolo_results(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, n_candidates, e->stream);
+}
+
+int adas_yolo_postprocess(int device, const float* raw_host, int model_kind, int batch, int n_anchors, int n_classes, int in_h,
+                          int in_w, int src_h, int src_w, double box_score, double nms_iou, int max_det, float* boxes_xywh,
+                          float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts, int32_t* n_candidates) {
+    ADAS_CUDA(cudaSetDevice(device));
+    const size_t per = model_kind == ADAS_MODEL_YOLOV8 ? (size_t)(4 + n_classes) * n_anchors : (size_t)n_anchors * (5 + n_classes);
+    float* d_raw = nullptr;
+    ADAS_CUDA(cudaMalloc(&d_raw, (size_t)batch * per * 4));
+    ADAS_CUDA(cudaMemcpy(d_raw, raw_host, (size_t)batch * per * 4, cudaMemcpyHostToDevice));
+    YoloPostBufs w{};
+    int rc = alloc_yolo_post(&w, batch, n_anchors, max_det);
+    const LetterboxGeom g = letterbox_geom(src_h, src_w, in_h, in_w);
+    if (!rc) rc = launch_yolo_post(d_raw, model_kind, batch, n_anchors, n_classes, g, box_score, nms_iou, max_det, w, 0);
+    if (!rc) rc = copy_yolo_results(w, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, n_candidates, 0);
+    free_yolo_post(&w);
+    cudaFree(d_raw);
+    return rc;
+}
+
+int adas_yolo_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W, int in_h, int in_w, float* blob) {
+    ADAS_CUDA(cudaSetDevice(device));
+    uint8_t* d_fr = nullptr; float* d_blob = nullptr;
+    const size_t fb = (size_t)batch * H * W * 3, bb = (size_t)batch * 3 * in_h * in_w * 4;
+    ADAS_CUDA(cudaMalloc(&d_fr, fb));
+    ADAS_CUDA(cudaMalloc(&d_blob, bb));
+    ADAS_CUDA(cudaMemcpy(d_fr, frames_host, fb, cudaMemcpyHostToDevice));
+    const LetterboxGeom g = letterbox_geom(H, W, in_h, in_w);
+    int rc = launch_yolo_pre(d_fr, batch, g, nullptr, 0, d_blob, 0);
+    if (!rc) { cudaError_t ce = cudaMemcpy(blob, d_blob, bb, cudaMemcpyDeviceToHost); if (ce != cudaSuccess) { set_error("D2H failed: %s", cudaGetErrorString(ce)); rc = 1; } }
+    cudaFree(d_fr); cudaFree(d_blob);
+    return rc;
+}
+
+int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device, int batch, int H, int W, int32_t* pts, int32_t* npts,
+                     uint8_t* status, double* coords_f) {
+    ADAS_CHECK(e != nullptr, "null engine");
+    ADAS_CHECK(e->hdr.model_kind == ADAS_MODEL_UFLDV2, "adas_ufld_detect on a YOLO plan");
+    ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const uint8_t* dfr = nullptr;
+    if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
+    const int in_h = (int)e->hdr.in_h, in_w = (int)e->hdr.in_w;
+    const int resize_h = (int)((double)in_h / 0.6);   // int(self.input_height / cfg.crop_ratio), CULane crop_ratio 0.6
+    if (launch_ufld_pre(dfr, batch, H, W, in_h, in_w, resize_h, e->d_lut, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr,
+                        e->stream)) return 1;
+    if (run_plan(e, batch)) return 1;
+    const uint32_t* m = e->hdr.meta;
+    UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
+    const PlanOutput& o = e->outs[0];
+    const float* heads = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
+    const int mp = e->ufld_max_pts;
+    if (launch_ufld_post(heads, (int)e->bufs[o.buffer].C, batch, d, W, H, e->d_row_anchor, e->d_col_anchor, e->d_pts, e->d_npts, e->d_status,
+                         coords_f ? e->d_coords : nullptr, mp, e->stream)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(pts, e->d_pts, (size_t)batch * 4 * mp * 2 * 4, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaMemcpyAsync(npts, e->d_npts, (size_t)batch * 4 * 4, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (coords_f) ADAS_CUDA(cudaMemcpyAsync(coords_f, e->d_coords, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int adas_ufld_postprocess(int device, const float* heads_host, int batch, int ngr, int ncr, int ngc, int ncc, int nl, int img_w, int img_h,
+                          const double* row_anchor, const double* col_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords_f) {
+    ADAS_CUDA(cudaSetDevice(device));
+    const size_t total = (size_t)ngr * ncr * nl + (size_t)ngc * ncc * nl + 2 * (size_t)ncr * nl + 2 * (size_t)ncc * nl;
+    const int mp = ncr > ncc ? ncr : ncc;
+    float* d_h = nullptr; double *d_ra = nullptr, *d_ca = nullptr, *d_co = nullptr; int32_t *d_p = nullptr, *d_n = nullptr; uint8_t* d_s = nullptr;
+    ADAS_CUDA(cudaMalloc(&d_h, (size_t)batch * total * 4));
+    ADAS_CUDA(cudaMalloc(&d_ra, ncr * 8)); ADAS_CUDA(cudaMalloc(&d_ca, ncc * 8));
+    ADAS_CUDA(cudaMalloc(&d_p, (size_t)batch * 4 * mp * 8)); ADAS_CUDA(cudaMalloc(&d_n, (size_t)batch * 16)); ADAS_CUDA(cudaMalloc(&d_s, (size_t)batch * 4));
+    ADAS_CUDA(cudaMalloc(&d_co, (size_t)batch * 4 * mp * 8));
+    ADAS_CUDA(cudaMemcpy(d_h, heads_host, (size_t)batch * total * 4, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_ra, row_anchor, ncr * 8, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_ca, col_anchor, ncc * 8, cudaMemcpyHostToDevice));
+    UfldDims d{ngr, ncr, ngc, ncc, nl};
+    int rc = launch_ufld_post(d_h, (int)total, batch, d, img_w, img_h, d_ra, d_ca, d_p, d_n, d_s, d_co, mp, 0);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpy(pts, d_p, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(npts, d_n, (size_t)batch * 16, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(status, d_s, (size_t)batch * 4, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && coords_f) ce = cudaMemcpy(coords_f, d_co, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { set_error("ufld_postprocess D2H: %s", cudaGetErrorString(ce)); rc = 1; }
+    }
+    cudaFree(d_h); cudaFree(d_ra); cudaFree(d_ca); cudaFree(d_p); cudaFree(d_n); cudaFree(d_s); cudaFree(d_co);
+    return rc;
+}
+
+int adas_ufld_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W, int in_h, int in_w, double crop_ratio, float* blob) {
+    ADAS_CUDA(cudaSetDevice(device));
+    uint8_t* d_fr = nullptr; float* d_blob = nullptr; float* d_lut = nullptr;
+    const size_t fb = (size_t)batch * H * W * 3, bb = (size_t)batch * 3 * in_h * in_w * 4;
+    float lut[768];
+    ufld_lut_host(lut);
+    ADAS_CUDA(cudaMalloc(&d_fr, fb)); ADAS_CUDA(cudaMalloc(&d_blob, bb)); ADAS_CUDA(cudaMalloc(&d_lut, sizeof(lut)));
+    ADAS_CUDA(cudaMemcpy(d_fr, frames_host, fb, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    const int resize_h = (int)((double)in_h / crop_ratio);
+    int rc = launch_ufld_pre(d_fr, batch, H, W, in_h, in_w, resize_h, d_lut, nullptr, 0, d_blob, 0);
+    if (!rc) { cudaError_t ce = cudaMemcpy(blob, d_blob, bb, cudaMemcpyDeviceToHost); if (ce != cudaSuccess) { set_error("D2H failed: %s", cudaGetErrorString(ce)); rc = 1; } }
+    cudaFree(d_fr); cudaFree(d_blob); cudaFree(d_lut);
+    return rc;
+}
+
+int adas_iou_cost(int device, int problems, const double* a_tlbr, const int32_t* a_off, const double* b_tlbr, const int32_t* b_off,
+                  const double* det_scores, int fuse, double* cost, const int64_t* cost_off) {
+    if (problems <= 0) return 0;
+    ADAS_CUDA(cudaSetDevice(device));
+    const int na = a_off[problems], nb = b_off[problems];
+    const int64_t ncost = cost_off[problems];
+    if (ncost == 0) return 0;
+    double *d_a = nullptr, *d_b = nullptr, *d_s = nullptr, *d_c = nullptr; int32_t *d_ao = nullptr, *d_bo = nullptr; int64_t* d_co = nullptr;
+    ADAS_CUDA(cudaMalloc(&d_a, (size_t)(na > 0 ? na : 1) * 32)); ADAS_CUDA(cudaMalloc(&d_b, (size_t)(nb > 0 ? nb : 1) * 32));
+    ADAS_CUDA(cudaMalloc(&d_s, (size_t)(nb > 0 ? nb : 1) * 8)); ADAS_CUDA(cudaMalloc(&d_c, (size_t)ncost * 8));
+    ADAS_CUDA(cudaMalloc(&d_ao, (problems + 1) * 4)); ADAS_CUDA(cudaMalloc(&d_bo, (problems + 1) * 4)); ADAS_CUDA(cudaMalloc(&d_co, (problems + 1) * 8));
+    ADAS_CUDA(cudaMemcpy(d_a, a_tlbr, (size_t)na * 32, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_b, b_tlbr, (size_t)nb * 32, cudaMemcpyHostToDevice));
+    if (fuse) ADAS_CUDA(cudaMemcpy(d_s, det_scores, (size_t)nb * 8, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_ao, a_off, (problems + 1) * 4, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_bo, b_off, (problems + 1) * 4, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_co, cost_off, (problems + 1) * 8, cudaMemcpyHostToDevice));
+    int rc = launch_iou_cost(problems, d_a, d_ao, d_b, d_bo, fuse ? d_s : nullptr, fuse, d_c, d_co, 0);
+    if (!rc) { cudaError_t ce = cudaMemcpy(cost, d_c, (size_t)ncost * 8, cudaMemcpyDeviceToHost); if (ce != cudaSuccess) { set_error("iou_cost D2H: %s", cudaGetErrorString(ce)); rc = 1; } }
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_s); cudaFree(d_c); cudaFree(d_ao); cudaFree(d_bo); cudaFree(d_co);
+    return rc;
+}
+
+int adas_lap(int device, int problems, const double* cost, const int64_t* cost_off, const int32_t* T, const int32_t* D, const double* thresh,
+             int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off) {
+    if (problems <= 0) return 0;
+    ADAS_CUDA(cudaSetDevice(device));
+    const int64_t ncost = cost_off[problems];
+    const int nx = x_off[problems], ny = y_off[problems];
+    for (int i = 0; i < problems; ++i) ADAS_CHECK(T[i] + D[i] <= lap_max_cols() && T[i] <= lap_max_cols() / 2, "adas_lap: problem %d too large (T=%d D=%d)", i, T[i], D[i]);
+    double *d_c = nullptr, *d_th = nullptr, *d_v = nullptr, *d_mv = nullptr; int64_t* d_co = nullptr;
+    int32_t *d_T = nullptr, *d_D = nullptr, *d_x = nullptr, *d_y = nullptr, *d_xo = nullptr, *d_yo = nullptr, *d_wi = nullptr;
+    const size_t wc = (size_t)lap_max_cols() + 1;
+    ADAS_CUDA(cudaMalloc(&d_c, (size_t)(ncost > 0 ? ncost : 1) * 8)); ADAS_CUDA(cudaMalloc(&d_th, problems * 8));
+    ADAS_CUDA(cudaMalloc(&d_v, problems * wc * 8)); ADAS_CUDA(cudaMalloc(&d_mv, problems * wc * 8)); ADAS_CUDA(cudaMalloc(&d_wi, problems * wc * 12));
+    ADAS_CUDA(cudaMalloc(&d_co, (problems + 1) * 8)); ADAS_CUDA(cudaMalloc(&d_T, problems * 4)); ADAS_CUDA(cudaMalloc(&d_D, problems * 4));
+    ADAS_CUDA(cudaMalloc(&d_x, (size_t)(nx > 0 ? nx : 1) * 4)); ADAS_CUDA(cudaMalloc(&d_y, (size_t)(ny > 0 ? ny : 1) * 4));
+    ADAS_CUDA(cudaMalloc(&d_xo, (problems + 1) * 4)); ADAS_CUDA(cudaMalloc(&d_yo, (problems + 1) * 4));
+    ADAS_CUDA(cudaMemcpy(d_c, cost, (size_t)ncost * 8, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_th, thresh, problems * 8, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_co, cost_off, (problems + 1) * 8, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_T, T, problems * 4, cudaMemcpyHostToDevice)); ADAS_CUDA(cudaMemcpy(d_D, D, problems * 4, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_xo, x_off, (problems + 1) * 4, cudaMemcpyHostToDevice)); ADAS_CUDA(cudaMemcpy(d_yo, y_off, (problems + 1) * 4, cudaMemcpyHostToDevice));
+    int rc = launch_lap(problems, d_c, d_co, d_T, d_D, d_th, d_x, d_xo, d_y, d_yo, d_v, d_mv, d_wi, 0);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpy(x, d_x, (size_t)nx * 4, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(y, d_y, (size_t)ny * 4, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { set_error("adas_lap D2H: %s", cudaGetErrorString(ce)); rc = 1; }
+    }
+    cudaFree(d_c); cudaFree(d_th); cudaFree(d_v); cudaFree(d_mv); cudaFree(d_wi); cudaFree(d_co); cudaFree(d_T); cudaFree(d_D);
+    cudaFree(d_x); cudaFree(d_y); cudaFree(d_xo); cudaFree(d_yo);
+    return rc;
+}
+
+// persistent per-thread scratch for the single-problem association path (tracker hot loop)
+struct AssocScratch {
+    int device = -1; size_t cap_boxes = 0; size_t cap_cost = 0;
+    double *d_a = nullptr, *d_b = nullptr, *d_s = nullptr, *d_c = nullptr, *d_th = nullptr, *d_v = nullptr, *d_mv = nullptr;
+    int32_t *d_meta = nullptr, *d_x = nullptr, *d_y = nullptr, *d_wi = nullptr; int64_t* d_co = nullptr;
+    cudaStream_t st = nullptr;
+};
+static thread_local AssocScratch g_as;
+
+int adas_associate(int device, int T, int D, const double* a_tlbr, const double* b_tlbr, const double* det_scores, int fuse, double thresh,
+                   int32_t* x, int32_t* y, double* cost_out) {
+    for (int i = 0; i < T; ++i) x[i] = -1;
+    for (int j = 0; j < D; ++j) y[j] = -1;
+    if (T == 0 || D == 0) return 0;   // matching.linear_assignment's empty-matrix short circuit (matching.py:21-22)
+    ADAS_CHECK(T + D <= lap_max_cols() && T <= lap_max_cols() / 2, "adas_associate: problem too large (T=%d D=%d)", T, D);
+    ADAS_CUDA(cudaSetDevice(device));
+    AssocScratch& s = g_as;
+    const size_t nb = (size_t)(T > D ? T : D), nc = (size_t)T * D;
+    if (s.device != device || nb > s.cap_boxes || nc > s.cap_cost) {
+        if (s.st == nullptr || s.device != device) { ADAS_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); }
+        cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_s); cudaFree(s.d_c); cudaFree(s.d_x); cudaFree(s.d_y);
+        s.cap_boxes = nb < 256 ? 256 : nb * 2; s.cap_cost = nc < 65536 ? 65536 : nc * 2;
+        ADAS_CUDA(cudaMalloc(&s.d_a, s.cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&s.d_b, s.cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&s.d_s, s.cap_boxes * 8));
+        ADAS_CUDA(cudaMalloc(&s.d_c, s.cap_cost * 8)); ADAS_CUDA(cudaMalloc(&s.d_x, s.cap_boxes * 4)); ADAS_CUDA(cudaMalloc(&s.d_y, s.cap_boxes * 4));
+        if (s.d_th == nullptr || s.device != device) {
+            const size_t wc = (size_t)lap_max_cols() + 1;
+            ADAS_CUDA(cudaMalloc(&s.d_th, 8)); ADAS_CUDA(cudaMalloc(&s.d_v, wc * 8)); ADAS_CUDA(cudaMalloc(&s.d_mv, wc * 8)); ADAS_CUDA(cudaMalloc(&s.d_wi, wc * 12));
+            ADAS_CUDA(cudaMalloc(&s.d_meta, 8 * 4)); ADAS_CUDA(cudaMalloc(&s.d_co, 2 * 8));
+        }
+        s.device = device;
+    }
+    // meta: [a_off0,a_off1,b_off0,b_off1,T,D,x_off0,-]  (x_off/y_off are both {0,..})
+    const int32_t meta[8] = {0, T, 0, D, T, D, 0, 0};
+    const int64_t co[2] = {0, (int64_t)nc};
+    ADAS_CUDA(cudaMemcpyAsync(s.d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, s.st));
+    ADAS_CUDA(cudaMemcpyAsync(s.d_co, co, sizeof(co), cudaMemcpyHostToDevice, s.st));
+    ADAS_CUDA(cudaMemcpyAsync(s.d_a, a_tlbr, (size_t)T * 32, cudaMemcpyHostToDevice, s.st));
+    ADAS_CUDA(cudaMemcpyAsync(s.d_b, b_tlbr, (size_t)D * 32, cudaMemcpyHostToDevice, s.st));
+    if (fuse) ADAS_CUDA(cudaMemcpyAsync(s.d_s, det_scores, (size_t)D * 8, cudaMemcpyHostToDevice, s.st));
+    ADAS_CUDA(cudaMemcpyAsync(s.d_th, &thresh, 8, cudaMemcpyHostToDevice, s.st));
+    if (launch_iou_cost(1, s.d_a, s.d_meta, s.d_b, s.d_meta + 2, fuse ? s.d_s : nullptr, fuse, s.d_c, s.d_co, s.st)) return 1;
+    if (launch_lap(1, s.d_c, s.d_co, s.d_meta + 4, s.d_meta + 5, s.d_th, s.d_x, s.d_meta + 6, s.d_y, s.d_meta + 6, s.d_v, s.d_mv, s.d_wi, s.st)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(x, s.d_x, (size_t)T * 4, cudaMemcpyDeviceToHost, s.st));
+    ADAS_CUDA(cudaMemcpyAsync(y, s.d_y, (size_t)D * 4, cudaMemcpyDeviceToHost, s.st));
+    if (cost_out) ADAS_CUDA(cudaMemcpyAsync(cost_out, s.d_c, nc * 8, cudaMemcpyDeviceToHost, s.st));
+    ADAS_CUDA(cudaStreamSynchronize(s.st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// track.cu -- ByteTrack association kernels (compiled with -fmad=false; float64 like the reference).
+//
+// Replaces (ObjectTracker/byteTrack/matching.py):
+//   ious / iou_distance   :34-80    iou = wh / (a1 + a2 - wh), no "+1" convention; cost = 1 - iou
+//   fuse_score            :108-116  cost = 1 - (1 - cost) * det_score[j]
+//   linear_assignment     :20-31    lap.lapjv(cost, extend_cost=True, cost_limit=thresh): the exact optimum of the
+//                                   (T+D)x(T+D) extended problem == min over partial matchings of
+//                                   sum(cost[matched]) + thresh/2 * (#unmatched rows + #unmatched cols).
+// `lap` is an un-vendored third-party C extension (requirements.txt:4, unpinned); the solver here is a
+// shortest-augmenting-path (Jonker-Volgenant / Hungarian with potentials) on the equivalent rectangular
+// problem: T rows x (D real + T private dummy) columns, real cost c - thresh, own dummy cost 0.
+// One warp per problem; the column scan of each Dijkstra step is lane-parallel with a deterministic
+// (lowest column) argmin.
+#include "common.h"
+
+namespace adas {
+
+__global__ void iou_cost_kernel(const double* __restrict__ a, const int32_t* __restrict__ a_off, const double* __restrict__ bxs,
+                                const int32_t* __restrict__ b_off, const double* __restrict__ det_scores, int fuse,
+                                double* __restrict__ cost, const int64_t* __restrict__ cost_off) {
+    const int pr = blockIdx.x;
+    const int T = a_off[pr + 1] - a_off[pr];
+    const int D = b_off[pr + 1] - b_off[pr];
+    const double* A = a + (size_t)a_off[pr] * 4;
+    const double* Bx = bxs + (size_t)b_off[pr] * 4;
+    const double* sc = det_scores ? det_scores + b_off[pr] : nullptr;
+    double* C = cost + cost_off[pr];
+    for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+        const int t = i / D, dd = i % D;
+        const double ax1 = A[t * 4], ay1 = A[t * 4 + 1], ax2 = A[t * 4 + 2], ay2 = A[t * 4 + 3];
+        const double bx1 = Bx[dd * 4], by1 = Bx[dd * 4 + 1], bx2 = Bx[dd * 4 + 2], by2 = Bx[dd * 4 + 3];
+        const double xx1 = fmax(ax1, bx1), yy1 = fmax(ay1, by1);
+        const double xx2 = fmin(ax2, bx2), yy2 = fmin(ay2, by2);
+        const double w = fmax(0.0, __dsub_rn(xx2, xx1));
+        const double h = fmax(0.0, __dsub_rn(yy2, yy1));
+        const double wh = __dmul_rn(w, h);
+        const double aa = __dmul_rn(__dsub_rn(ax2, ax1), __dsub_rn(ay2, ay1));
+        const double ab = __dmul_rn(__dsub_rn(bx2, bx1), __dsub_rn(by2, by1));
+        const double iou = __ddiv_rn(wh, __dsub_rn(__dadd_rn(aa, ab), wh));
+        double c = __dsub_rn(1.0, iou);
+        if (fuse) {
+            const double sim = __dsub_rn(1.0, c);
+            c = __dsub_rn(1.0, __dmul_rn(sim, sc[dd]));
+        }
+        C[i] = c;
+    }
+}
+
+int launch_iou_cost(int problems, const double* a, const int32_t* a_off, const double* b, const int32_t* b_off,
+                    const double* det_scores, int fuse, double* cost, const int64_t* cost_off, cudaStream_t st) {
+    iou_cost_kernel<<<problems, 256, 0, st>>>(a, a_off, b, b_off, det_scores, fuse, cost, cost_off);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static constexpr int LAP_MAX_COLS = 2048;   // D + T
+
+__device__ __forceinline__ double lap_cost(const double* C, int D, int T, double thresh, int i, int j) {
+    // i in [0,T), j in [0, D+T)
+    if (j < D) return __dsub_rn(C[(size_t)i * D + j], thresh);
+    return (j - D == i) ? 0.0 : 1e300;
+}
+
+__global__ void lap_kernel(const double* __restrict__ cost, const int64_t* __restrict__ cost_off, const int32_t* __restrict__ Ts,
+                           const int32_t* __restrict__ Ds, const double* __restrict__ threshs, int32_t* __restrict__ x,
+                           const int32_t* __restrict__ x_off, int32_t* __restrict__ y, const int32_t* __restrict__ y_off,
+                           double* __restrict__ work_v, double* __restrict__ work_minv, int32_t* __restrict__ work_i) {
+    // one warp per problem (blockDim = 32)
+    const int pr = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int T = Ts[pr], D = Ds[pr];
+    const int m = D + T;
+    const double thresh = threshs[pr];
+    const double* C = cost + cost_off[pr];
+    int32_t* X = x + x_off[pr];
+    int32_t* Y = y + y_off[pr];
+    // per-problem scratch (global, L1/L2 resident): column potentials v, minv, p (row matched to column), way, used
+    double* v = work_v + (size_t)pr * (LAP_MAX_COLS + 1);
+    double* minv = work_minv + (size_t)pr * (LAP_MAX_COLS + 1);
+    int32_t* p = work_i + (size_t)pr * 3 * (LAP_MAX_COLS + 1);   // p[j]: 1-based row matched to column j (0 = free)
+    int32_t* way = p + (LAP_MAX_COLS + 1);
+    int32_t* used = way + (LAP_MAX_COLS + 1);
+    __shared__ double u[LAP_MAX_COLS / 2 + 1];   // row potentials (T <= 1024)
+    for (int j = lane; j <= m; j += 32) { v[j] = 0.0; p[j] = 0; way[j] = 0; }
+    for (int i = lane; i <= T; i += 32) u[i] = 0.0;
+    __syncwarp();
+    // columns are 1-based internally (column 0 is the virtual start), rows 1-based
+    for (int i = 1; i <= T; ++i) {
+        if (lane == 0) p[0] = i;
+        for (int j = lane; j <= m; j += 32) { minv[j] = 1e308; used[j] = 0; }
+        __syncwarp();
+        int j0 = 0;
+        while (true) {
+            if (lane == 0) used[j0] = 1;
+            __syncwarp();
+            const int i0 = p[j0];
+            const double ui0 = u[i0];
+            double bd = 1e308; int bj = 0x7fffffff;
+            for (int j = 1 + lane; j <= m; j += 32) {
+                if (!used[j]) {
+                    const double cur = __dsub_rn(__dsub_rn(lap_cost(C, D, T, thresh, i0 - 1, j - 1), ui0), v[j]);
+                    if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+                    const double mv = minv[j];
+                    if (mv < bd) { bd = mv; bj = j; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+            }
+            const double delta = bd;
+            const int j1 = bj;
+            for (int j = lane; j <= m; j += 32) {
+                if (used[j]) { u[p[j]] = __dadd_rn(u[p[j]], delta); v[j] = __dsub_rn(v[j], delta); }
+                else minv[j] = __dsub_rn(minv[j], delta);
+            }
+            __syncwarp();
+            j0 = j1;
+            if (p[j0] == 0) break;
+        }
+        // augment along the alternating path
+        if (lane == 0) {
+            while (j0 != 0) {
+                const int j1 = way[j0];
+                p[j0] = p[j1];
+                j0 = j1;
+            }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < T; i += 32) X[i] = -1;
+    for (int j = lane; j < D; j += 32) Y[j] = -1;
+    __syncwarp();
+    for (int j = 1 + lane; j <= D; j += 32) {
+        const int r = p[j];
+        if (r != 0) { X[r - 1] = j - 1; Y[j - 1] = r - 1; }
+    }
+}
+
+int launch_lap(int problems, const double* cost, const int64_t* cost_off, const int32_t* T, const int32_t* D,
+               const double* thresh, int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off, double* work_v,
+               double* work_minv, int32_t* work_i, cudaStream_t st) {
+    lap_kernel<<<problems, 32, 0, st>>>(cost, cost_off, T, D, thresh, x, x_off, y, y_off, work_v, work_minv, work_i);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lap_max_cols() { return LAP_MAX_COLS; }
+
+}  // namespace adas

@@ -150,6 +150,23 @@ int adas_associate(int device, int T, int D, const double* a_tlbr, const double*
                    const double* det_scores, int fuse, double thresh, int32_t* x, int32_t* y,
                    double* cost_out);
 
+/* ---- test hooks (no reference counterpart): raw access to the plan's activation buffers so single kernels can be
+ * parity-tested.  Buffers are [batch * rows_per_img, C] matrices (fp16 or fp32) as described in csrc/plan.h. */
+int adas_engine_num_buffers(const adas_engine* e, int* n);
+int adas_engine_buffer_info(const adas_engine* e, int idx, int64_t info[5] /* rows_per_img, C, dtype, H, W */);
+int adas_engine_write_buffer(adas_engine* e, int idx, const void* host, int64_t bytes);
+int adas_engine_read_buffer(adas_engine* e, int idx, void* host, int64_t bytes);
+int adas_engine_run(adas_engine* e, int batch);   /* replay the plan on whatever buffer 0 holds; synchronous */
+
+/* ---- timing hooks (bench.py): CUDA events on the handle's own stream (torch.cuda.Event only sees torch's stream).
+ * adas_engine_event_record records event `slot` (0..3) on e's stream; adas_event_elapsed_ms synchronises on both
+ * events and returns the time between (ea, slot_a) and (eb, slot_b).  adas_engine_time_ops replays, `iters` times and
+ * back to back between two events, only the plan ops whose type bit (1 << PlanOpType) is set in type_mask, and
+ * returns the average milliseconds per replay plus the number of kernel launches per replay. */
+int adas_engine_event_record(adas_engine* e, int slot);
+int adas_event_elapsed_ms(adas_engine* ea, int slot_a, adas_engine* eb, int slot_b, float* ms);
+int adas_engine_time_ops(adas_engine* e, int batch, unsigned type_mask, int iters, float* ms_per_iter, int* launches);
+
 /* ---- optional multi-GPU gather -------------------------------------------------------------
  * (no reference counterpart: the reference is single-GPU)  The gather of
  * fixed-size detection records across ranks is done with torch.distributed (NCCL) in the

@@ -22,7 +22,8 @@ SYMBOLS = [
     "adas_engine_model_kind", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
-    "adas_engine_stream",
+    "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
+    "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops",
 ]
 
 
@@ -87,6 +88,39 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ---- test hooks -------------------------------------------------------------------------
+    def buffer_info(self, idx: int):
+        info = (C.c_int64 * 5)()
+        check(lib().adas_engine_buffer_info(self._h, idx, info))
+        return dict(rows_per_img=int(info[0]), C=int(info[1]), dtype=np.float32 if info[2] == 1 else np.float16, H=int(info[3]), W=int(info[4]))
+
+    def write_buffer(self, idx: int, arr: np.ndarray) -> None:
+        arr = np.ascontiguousarray(arr)
+        check(lib().adas_engine_write_buffer(self._h, idx, arr.ctypes.data_as(C.c_void_p), C.c_int64(arr.nbytes)))
+
+    def read_buffer(self, idx: int, batch: int) -> np.ndarray:
+        bi = self.buffer_info(idx)
+        out = np.empty((batch * bi["rows_per_img"], bi["C"]), bi["dtype"])
+        check(lib().adas_engine_read_buffer(self._h, idx, out.ctypes.data_as(C.c_void_p), C.c_int64(out.nbytes)))
+        return out
+
+    def run(self, batch: int) -> None:
+        check(lib().adas_engine_run(self._h, batch))
+
+    # ---- timing hooks ------------------------------------------------------------------------
+    def event_record(self, slot: int) -> None:
+        check(lib().adas_engine_event_record(self._h, slot))
+
+    def elapsed_ms(self, slot_a: int, other: "Engine", slot_b: int) -> float:
+        ms = C.c_float()
+        check(lib().adas_event_elapsed_ms(self._h, slot_a, other._h, slot_b, C.byref(ms)))
+        return float(ms.value)
+
+    def time_ops(self, batch: int, type_mask: int, iters: int):
+        ms, n = C.c_float(), C.c_int()
+        check(lib().adas_engine_time_ops(self._h, batch, C.c_uint(type_mask), iters, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     # engine_inference: fp32 NCHW host -> list of fp32 host arrays
     def infer(self, x: np.ndarray):

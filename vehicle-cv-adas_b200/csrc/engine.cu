@@ -40,6 +40,7 @@ struct DevBuf {
 
 struct Program {   // launch list for one batch size
     std::vector<std::function<int(cudaStream_t)>> steps;
+    std::vector<uint32_t> step_type;
     cudaGraphExec_t graph = nullptr;
     int runs = 0;
 };
@@ -77,6 +78,7 @@ struct adas_engine {
     double* d_col_anchor = nullptr;
     int32_t* d_pts = nullptr; int32_t* d_npts = nullptr; uint8_t* d_status = nullptr; double* d_coords = nullptr;
     int ufld_max_pts = 0;
+    cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace adas {
@@ -92,6 +94,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
     for (size_t oi = 0; oi < e->ops.size(); ++oi) {
         const PlanOp& op = e->ops[oi];
         const int32_t* p = op.p;
+        prog->step_type.push_back(op.type);
         switch (op.type) {
             case OP_GEMM: {
                 const int a_buf = p[0], a_coff = p[1], Kc = p[2], ntaps = p[3], w_t = p[4], bias_t = p[5], N = p[6], act = p[7];
@@ -658,6 +661,81 @@ int adas_lap(int device, int problems, const double* cost, const int64_t* cost_o
     cudaFree(d_c); cudaFree(d_th); cudaFree(d_v); cudaFree(d_mv); cudaFree(d_wi); cudaFree(d_co); cudaFree(d_T); cudaFree(d_D);
     cudaFree(d_x); cudaFree(d_y); cudaFree(d_xo); cudaFree(d_yo);
     return rc;
+}
+
+int adas_engine_num_buffers(const adas_engine* e, int* n) { *n = (int)e->bufs.size(); return 0; }
+int adas_engine_buffer_info(const adas_engine* e, int idx, int64_t info[5]) {
+    ADAS_CHECK(idx >= 0 && idx < (int)e->bufs.size(), "bad buffer index %d", idx);
+    const PlanBuffer& b = e->bufs[idx];
+    info[0] = b.rows_per_img; info[1] = b.C; info[2] = b.dtype; info[3] = b.H; info[4] = b.W;
+    return 0;
+}
+int adas_engine_write_buffer(adas_engine* e, int idx, const void* host, int64_t bytes) {
+    ADAS_CHECK(idx >= 0 && idx < (int)e->bufs.size() && (size_t)bytes <= e->dbufs[idx].bytes, "bad buffer write (idx %d, %lld bytes)", idx, (long long)bytes);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    ADAS_CUDA(cudaMemcpyAsync(e->dbufs[idx].ptr, host, (size_t)bytes, cudaMemcpyHostToDevice, e->stream));
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int adas_engine_read_buffer(adas_engine* e, int idx, void* host, int64_t bytes) {
+    ADAS_CHECK(idx >= 0 && idx < (int)e->bufs.size() && (size_t)bytes <= e->dbufs[idx].bytes, "bad buffer read (idx %d, %lld bytes)", idx, (long long)bytes);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    ADAS_CUDA(cudaMemcpyAsync(host, e->dbufs[idx].ptr, (size_t)bytes, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int adas_engine_run(adas_engine* e, int batch) {
+    ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    if (run_plan(e, batch)) return 1;
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int adas_engine_event_record(adas_engine* e, int slot) {
+    ADAS_CHECK(e != nullptr && slot >= 0 && slot < 4, "bad event slot");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    if (e->events[slot] == nullptr) ADAS_CUDA(cudaEventCreate(&e->events[slot]));
+    ADAS_CUDA(cudaEventRecord(e->events[slot], e->stream));
+    return 0;
+}
+int adas_event_elapsed_ms(adas_engine* ea, int slot_a, adas_engine* eb, int slot_b, float* ms) {
+    ADAS_CHECK(ea && eb && ea->events[slot_a] && eb->events[slot_b], "events not recorded");
+    ADAS_CUDA(cudaEventSynchronize(ea->events[slot_a]));
+    ADAS_CUDA(cudaEventSynchronize(eb->events[slot_b]));
+    ADAS_CUDA(cudaEventElapsedTime(ms, ea->events[slot_a], eb->events[slot_b]));
+    return 0;
+}
+int adas_engine_time_ops(adas_engine* e, int batch, unsigned type_mask, int iters, float* ms_per_iter, int* launches) {
+    ADAS_CHECK(e != nullptr && batch >= 1 && batch <= e->max_batch && iters >= 1, "bad arguments");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    auto it = e->programs.find(batch);
+    if (it == e->programs.end()) {
+        Program prog;
+        if (build_program(e, batch, &prog)) return 1;
+        it = e->programs.emplace(batch, std::move(prog)).first;
+    }
+    Program& pg = it->second;
+    cudaEvent_t a, b;
+    ADAS_CUDA(cudaEventCreate(&a)); ADAS_CUDA(cudaEventCreate(&b));
+    int n = 0;
+    for (int warm = 0; warm < 2; ++warm) {
+        if (warm == 1) ADAS_CUDA(cudaEventRecord(a, e->stream));
+        const int reps = warm == 0 ? 1 : iters;
+        for (int r = 0; r < reps; ++r) {
+            n = 0;
+            for (size_t i = 0; i < pg.steps.size(); ++i)
+                if (type_mask & (1u << pg.step_type[i])) { if (pg.steps[i](e->stream)) return 1; ++n; }
+        }
+    }
+    ADAS_CUDA(cudaEventRecord(b, e->stream));
+    ADAS_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    ADAS_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_per_iter = ms / iters;
+    if (launches) *launches = n;
+    return 0;
 }
 
 // persistent per-thread scratch for the single-problem association path (tracker hot loop)

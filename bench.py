@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- end-to-end frames/s of the per-frame ADAS path (YOLOv8l + UFLDv2-CULane-ResNet34 + ByteTrack) on
+synthetic 1280x720 frames, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 8] [--impl b200|reference]
+
+A "step" = one batch of `--batch` consecutive frames of one stream through the whole hot path:
+    frames -> [letterbox + YOLOv8l + DFL decode + candidate select + reference NMS]  (adas_yolo_detect)
+           -> [resize/crop/normalise + UFLDv2-res34 + row/col-anchor decode]         (adas_ufld_detect)
+           -> ByteTrack update per frame, in order (device IoU-cost + LAP kernels)   (BYTETracker.update)
+`value`  : frames already resident in HBM (device pointers), timed with CUDA events on the engines' own streams.
+`e2e`    : the same steps fed from pinned HOST memory through the reference-facing API (H2D inside the timed region,
+           results read back to the host every step) -- the headline number.
+`--impl reference` times the oracle's CPU port of the reference path (reference Python semantics, torch-CPU fp32
+nets with the same seeded weights; onnxruntime is not installed, so ORT-CPU is substituted by torch-CPU) on a
+bounded sample.  Multi-GPU (torchrun): every rank runs its own stream (weak scaling); the only collective is an
+NCCL all_gather of the fixed-size detection records per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GFLOP_YOLOV8L = 165.1
+GFLOP_UFLD34 = 75.15
+FRAME_H, FRAME_W = 720, 1280
+BOX_SCORE, NMS_IOU, MAX_DET = 0.4, 0.45, 300
+CACHE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "adas_b200_plans")
+
+
+def synth_stream(seed: int, n: int) -> np.ndarray:
+    """n frames of a moving-rectangles scene over noise (SURVEY 8d synthetic inputs), uint8 BGR."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (FRAME_H, FRAME_W, 3), dtype=np.uint8)
+    k = 24
+    pos = rng.uniform(0, 1, (k, 2)) * (FRAME_W - 200, FRAME_H - 200)
+    vel = rng.uniform(-6, 6, (k, 2))
+    size = rng.integers(40, 260, (k, 2))
+    col = rng.integers(0, 256, (k, 3), dtype=np.uint8)
+    out = np.empty((n, FRAME_H, FRAME_W, 3), np.uint8)
+    for f in range(n):
+        img = base.copy()
+        for j in range(k):
+            x, y = (pos[j] + vel[j] * f).astype(int)
+            x, y = int(np.clip(x, 0, FRAME_W - 10)), int(np.clip(y, 0, FRAME_H - 10))
+            img[y:y + size[j, 1], x:x + size[j, 0]] = col[j]
+        out[f] = img
+    return out
+
+
+def build_plans(seed: int = 0):
+    import adas_b200  # noqa: F401
+    from adas_b200 import plan
+    os.makedirs(CACHE, exist_ok=True)
+    out = {}
+    for kind, builder, kw in (("yolov8", plan.build_yolov8, dict(scale="l")), ("ufldv2", plan.build_ufldv2, dict(backbone="34"))):
+        path = os.path.join(CACHE, f"bench_{kind}_s{seed}.b200w")
+        W = plan.synth_weights(kind, seed)
+        pb = builder(W, **kw)
+        if not os.path.isfile(path):
+            pb.write(path + f".{os.getpid()}.tmp")
+            os.replace(path + f".{os.getpid()}.tmp", path)
+        out[kind] = (path, W.state_dict, pb)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------------------
+class B200Pipeline:
+    def __init__(self, plans, device: int, batch: int):
+        from adas_b200 import _capi
+        from adas_b200.ObjectTracker import BYTETracker
+        self.capi = _capi
+        self.batch = batch
+        self.yolo = _capi.Engine(plans["yolov8"][0], device, max_batch=batch)
+        self.ufld = _capi.Engine(plans["ufldv2"][0], device, max_batch=batch)
+        self.tracker = BYTETracker(names=[], device=device)
+        self.tracker.reset()
+        self.last = None
+
+    def step(self, frames, on_device: bool, shape=None):
+        y = self.yolo.yolo_detect(frames, BOX_SCORE, NMS_IOU, MAX_DET, on_device=on_device, shape=shape)
+        u = self.ufld.ufld_detect(frames, on_device=on_device, shape=shape)
+        boxes, scores, cls, _, counts, _ = y
+        tracks = []
+        for b in range(self.batch):
+            n = int(counts[b])
+            bx = boxes[b, :n]
+            xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(int) if n else np.zeros((0, 4), int)
+            tracks.append(self.tracker.update(xyxy, scores[b, :n], cls[b, :n], None))
+        self.last = (y, u, tracks)
+        return y, u, tracks
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import adas_b200  # noqa: F401
+    from adas_b200 import _capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    if rank == 0:
+        plans = build_plans()
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        plans = build_plans()
+    pipe = B200Pipeline(plans, local, B)
+
+    # one stream per rank; frames differ per step (pool larger than L2: 24 batches x 22 MB = 530 MB >> 126 MB)
+    pool_batches = 24
+    stream = synth_stream(1000 + rank, B * 4)
+    host_pool = torch.empty((pool_batches, B, FRAME_H, FRAME_W, 3), dtype=torch.uint8).pin_memory()
+    hp = host_pool.numpy()
+    for i in range(pool_batches):
+        hp[i] = np.roll(stream[(i % 4) * B:(i % 4 + 1) * B], shift=3 * i, axis=2)
+    dev_pool = host_pool.to(f"cuda:{local}")
+    torch.cuda.synchronize()
+    gather_buf = torch.zeros((B, MAX_DET, 7), dtype=torch.float32, device=f"cuda:{local}")
+    gathered = [torch.zeros_like(gather_buf) for _ in range(world)] if world > 1 else None
+
+    def gather(y):
+        if world == 1:
+            return
+        boxes, scores, cls, _, counts, _ = y
+        rec = np.zeros((B, MAX_DET, 7), np.float32)
+        rec[..., :4], rec[..., 4], rec[..., 5] = boxes, scores, cls
+        gather_buf.copy_(torch.from_numpy(rec), non_blocking=True)
+        dist.all_gather(gathered, gather_buf)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(on_device: bool):
+        for i in range(Wm):
+            fr = dev_pool[i % pool_batches] if on_device else hp[i % pool_batches]
+            y, _, _ = pipe.step(fr.data_ptr() if on_device else fr, on_device, (B, FRAME_H, FRAME_W))
+            gather(y)
+        barrier()
+        n0 = _capi.launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        pipe.yolo.event_record(0)
+        t0 = time.perf_counter()
+        for i in range(K):
+            j = (Wm + i) % pool_batches
+            fr = dev_pool[j] if on_device else hp[j]
+            y, _, _ = pipe.step(fr.data_ptr() if on_device else fr, on_device, (B, FRAME_H, FRAME_W))
+            gather(y)
+        pipe.ufld.event_record(1)
+        torch.cuda.synchronize()
+        ms_dev = pipe.yolo.elapsed_ms(0, pipe.ufld, 1)
+        ms_wall = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        launches = _capi.launch_count() - n0
+        barrier()
+        # the tracker runs on the host after the last device event: take the larger of the two clocks
+        ms = max(ms_dev, ms_wall)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    ms_dev, launches, clocks = timed(True)
+    ms_e2e, _, clocks_e2e = timed(False)
+
+    result = None
+    if rank == 0:
+        fps = world * B * K / (ms_dev / 1e3)
+        fps_e2e = world * B * K / (ms_e2e / 1e3)
+        # roofline of the dominant kernel (gemm_tc_kernel): all GEMM launches of one step back to back on the engine stream
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        ms_y, n_y = pipe.yolo.time_ops(B, 1 << 1, 5)
+        ms_u, n_u = pipe.ufld.time_ops(B, 1 << 1, 5)
+        ms_all_y, _ = pipe.yolo.time_ops(B, 0xFFFFFFFF, 5)
+        ms_all_u, _ = pipe.ufld.time_ops(B, 0xFFFFFFFF, 5)
+        gflop_step = (GFLOP_YOLOV8L + GFLOP_UFLD34) * B
+        achieved = gflop_step / (ms_y + ms_u)          # GFLOP / ms == TFLOP/s
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cpu = cpu_baseline_sample(plans, frames=args.cpu_frames) if args.cpu_frames > 0 else None
+        result = {
+            "metric": "end-to-end frames/sec (YOLOv8l+UFLDv2+ByteTrack) 1280x720", "value": round(fps, 2), "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "YOLOv8l 640x640 + UFLDv2-CULane-ResNet34 320x1600 + ByteTrack, 1280x720 synthetic stream per GPU, "
+                                   f"batch {B} frames per step (BASELINE configs[3]; configs[4] when n_gpus=8)",
+                       "global_batch": world * B, "parallelism": f"dp{world} (one stream per GPU, NCCL all_gather of detection records)",
+                       "weights": "seeded synthetic (He-normal, BN folded), fp16 operands, fp32 accumulate",
+                       "l2": f"inputs rotate through a {pool_batches}-batch pool ({pool_batches * B * FRAME_H * FRAME_W * 3 / 1e6:.0f} MB > 126 MB L2)"},
+            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": 2 * B * FRAME_H * FRAME_W * 3,
+                    "d2h_bytes_per_step": int(B * (MAX_DET * (16 + 4 + 4 + 4) + 8) + B * (4 * 81 * 2 * 4 + 16 + 4)),
+                    "ms_per_step": round(ms_e2e / K, 4), "note": "each engine uploads the batch itself (YOLO and UFLD handles are independent)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; GEMM launches timed alone, of measured)" if peaks else "fallback 1590 (of fallback)",
+                         "launches_per_step": n_y + n_u, "avg_launch_us": round(1e3 * (ms_y + ms_u) / (n_y + n_u), 2),
+                         "algorithmic_gflop_per_step": round(gflop_step, 1),
+                         "gemm_ms_per_step": round(ms_y + ms_u, 4), "all_plan_kernels_ms_per_step": round(ms_all_y + ms_all_u, 4)},
+        }
+        if cpu is not None:
+            result["cpu_baseline"] = cpu
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the CPU port of the reference path (oracle) -- checker-as-baseline, never the product
+# ------------------------------------------------------------------------------------------------------------
+class CpuReferencePath:
+    def __init__(self, plans):
+        import torch
+        from oracle import nets, post, track
+        self.torch, self.post = torch, post
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.yolo = nets.build("yolov8", plans["yolov8"][1], scale="l")
+        self.ufld = nets.build("ufldv2", plans["ufldv2"][1], backbone="34")
+        self.trk = track.Tracker()
+        self.trk.reset()
+
+    def frame(self, img):
+        torch, post = self.torch, self.post
+        blob, geom = post.yolo_prepare_input(img, 640, 640)
+        with torch.no_grad():
+            raw = self.yolo(torch.from_numpy(blob)).numpy()[0]
+        det = post.yolo_postprocess(raw, "v8", geom, BOX_SCORE, NMS_IOU)
+        x = post.ufld_prepare_input(img, 320, 1600, 0.6)
+        with torch.no_grad():
+            heads = [o.numpy() for o in self.ufld(torch.from_numpy(x))]
+        lanes = post.ufld_decode(heads, img.shape[1], img.shape[0], post.CULANE_ROW_ANCHOR, post.CULANE_COL_ANCHOR)
+        b = det["boxes"]
+        xyxy = np.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2], b[:, 1] + b[:, 3]], 1).astype(int) if len(b) else np.zeros((0, 4), int)
+        self.trk.update(xyxy, det["scores"], det["cls"])
+        return det, lanes
+
+
+def cpu_baseline_sample(plans, frames: int = 8):
+    path = CpuReferencePath(plans)
+    imgs = synth_stream(1000, frames + 1)
+    path.frame(imgs[0])                     # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    for i in range(frames):
+        path.frame(imgs[1 + i])
+    dt = time.perf_counter() - t0
+    return {"value": round(frames / dt, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{frames} consecutive 1280x720 frames, batch 1 (the reference's only mode), oracle port: reference pre/post/tracker "
+                      "semantics in numpy + torch-CPU fp32 nets (onnxruntime absent -> torch-CPU substitutes ORT-CPU)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    plans = build_plans()
+    path = CpuReferencePath(plans)
+    per_step = args.ref_frames
+    K, Wm = args.steps, max(args.warmup, 1)
+    # bound the run to a few minutes: ~1 s of CPU per frame
+    K = min(K, max(3, int(150 / max(per_step, 1))))
+    Wm = min(Wm, 2)
+    imgs = synth_stream(1000, per_step * 4)
+    for i in range(Wm):
+        for f in range(per_step):
+            path.frame(imgs[(i * per_step + f) % len(imgs)])
+    t0 = time.perf_counter()
+    for i in range(K):
+        for f in range(per_step):
+            path.frame(imgs[((Wm + i) * per_step + f) % len(imgs)])
+    dt = time.perf_counter() - t0
+    fps = K * per_step / dt
+    sample = (f"each step = {per_step} consecutive 1280x720 frames at batch 1 through the oracle port of the reference path "
+              "(torch-CPU fp32 substitutes ONNXRuntime-CPU, which is not installed)")
+    print(json.dumps({
+        "impl": "reference", "metric": "end-to-end frames/sec (YOLOv8l+UFLDv2+ByteTrack) 1280x720", "value": round(fps, 3), "unit": "frames/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": Wm, "ms_per_step": round(dt / K * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "YOLOv8l 640x640 + UFLDv2-CULane-ResNet34 320x1600 + ByteTrack, 1280x720 synthetic stream (CPU, bounded sample)",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample (0 disables)")
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of the --impl reference arm")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

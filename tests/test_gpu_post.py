@@ -73,8 +73,8 @@ def test_yolo_post_vs_oracle_edge_cases(n_hot, thr, iou):
         assert np.array_equal(scores[b, :n], r["scores"])
         assert np.array_equal(cls[b, :n], r["cls"])
         dup += n != len(set(idx[b, :n].tolist()))
-    if n_hot >= 120:
-        assert dup > 0
+    if n_hot in (120, 300):
+        assert dup > 0      # the reference's duplicate-emitting swap path is exercised
 
 
 @pytest.mark.parametrize("hw", [(720, 1280), (480, 640)])

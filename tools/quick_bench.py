@@ -1,6 +1,6 @@
 """Scratch timing script for the first GPU runs (not the contract bench)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np
 import adas_b200
 from adas_b200 import _capi

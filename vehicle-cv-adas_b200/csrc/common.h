@@ -53,6 +53,8 @@ struct GemmParams {
     int out_ld;     // row stride of out, elements
     int res_ld;     // row stride of res, elements; NEGATIVE = add the residual before the activation (ResNet)
     int mask_H, mask_W;  // > 0: only rows in the interior of the padded (H+2)x(W+2) grid are stored
+    int dbg;        // debug switches (ADAS_B200_DBG), 0 in production
+    int mt_hint;    // v2 kernel: 1 forces single 128-row sub-tiles (more CTAs for small layers), 0 = auto
     int transposed; // 1: out[n * out_ld + row] (swap-AB FC: rows = features, cols = batch), bias per row
     const float* bias;   // [N] ([M] when transposed) or nullptr
     const __half* res;   // residual, same row indexing as out, or nullptr
@@ -62,6 +64,12 @@ struct GemmParams {
     const __half* Wt; int w_ld;
 };
 
+struct GemmV2;
+int  gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
+                        const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
+int  gemm_tc_v2_run(void* opaque, cudaStream_t st);
+void gemm_tc_v2_free(void* opaque);
+void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out);
 int  gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st);
 int  gemm_simt_launch(const GemmParams& p, cudaStream_t st);
 int  gemm_tc_smem_bytes(int BN, int stages);

@@ -54,6 +54,7 @@ struct adas_engine {
     int max_batch = 1;
     int conv_impl = 0;
     bool use_graph = true;
+    bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
     cudaStream_t stream = nullptr;
     PlanHeader hdr;
     std::vector<PlanBuffer> bufs;
@@ -113,20 +114,22 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 ADAS_CHECK((size_t)e->tensors[w_t].bytes >= (size_t)(transposed ? N : N) * Ktot * 2, "op %zu: weight tensor too small", oi);
                 const __half* aptr = static_cast<const __half*>(e->dbufs[a_buf].ptr) + a_coff;
                 const int a_rows = batch * (int)ab.rows_per_img;
-                CUtensorMap tmA, tmB;
+                const void *opA, *opB;
+                uint64_t a_inner, a_rows_u, a_stride, b_inner, b_rows_u, b_stride;
                 if (!transposed) {
                     g.M = a_rows;
                     g.N = N;
                     if (BN <= 0) {
-                        // widest tile that divides the work evenly: fewer, fatter CTAs keep smem traffic per MMA low
-                        if (N <= 256) BN = (N + 15) / 16 * 16;
+                        if (e->conv_impl == 0 && !e->gemm_v1) {
+                            gemm_tc_v2_choose(a_rows, N, Kc, ntaps, &BN, &g.mt_hint);
+                        } else if (N <= 256) BN = (N + 15) / 16 * 16;
                         else if (N % 256 == 0) BN = 256;
                         else if (N % 160 == 0) BN = 160;
                         else if (N % 128 == 0) BN = 128;
                         else BN = 256;
                     }
-                    if (make_tmap_2d(&tmA, aptr, (uint64_t)Kc, (uint64_t)a_rows, (uint64_t)ab.C * 2, 64, 128)) return 1;
-                    if (make_tmap_2d(&tmB, wptr, (uint64_t)Ktot, (uint64_t)N, (uint64_t)Ktot * 2, 64, (uint32_t)BN)) return 1;
+                    opA = aptr; a_inner = (uint64_t)Kc; a_rows_u = (uint64_t)a_rows; a_stride = (uint64_t)ab.C * 2;
+                    opB = wptr; b_inner = (uint64_t)Ktot; b_rows_u = (uint64_t)N; b_stride = (uint64_t)Ktot * 2;
                     g.A = aptr; g.a_ld = (int)ab.C; g.Wt = wptr; g.w_ld = Ktot;
                     g.out_ld = (int)ob.C;
                     ADAS_CHECK((int)ob.rows_per_img == (int)ab.rows_per_img, "op %zu: GEMM in/out row geometry differs", oi);
@@ -136,8 +139,8 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     g.N = a_rows;
                     BN = (a_rows + 15) / 16 * 16;
                     ADAS_CHECK(BN <= 256, "op %zu: transposed GEMM supports at most 256 activation rows", oi);
-                    if (make_tmap_2d(&tmA, wptr, (uint64_t)Ktot, (uint64_t)N, (uint64_t)Ktot * 2, 64, 128)) return 1;
-                    if (make_tmap_2d(&tmB, aptr, (uint64_t)Kc, (uint64_t)a_rows, (uint64_t)ab.C * 2, 64, (uint32_t)BN)) return 1;
+                    opA = wptr; a_inner = (uint64_t)Ktot; a_rows_u = (uint64_t)N; a_stride = (uint64_t)Ktot * 2;
+                    opB = aptr; b_inner = (uint64_t)Kc; b_rows_u = (uint64_t)a_rows; b_stride = (uint64_t)ab.C * 2;
                     g.A = wptr; g.a_ld = Ktot; g.Wt = aptr; g.w_ld = (int)ab.C;
                     g.out_ld = (int)ob.C;
                 }
@@ -153,8 +156,19 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 }
                 g.out = static_cast<uint8_t*>(e->dbufs[out_buf].ptr) + (size_t)out_coff * elem_size(ob.dtype);
                 if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
-                if (e->conv_impl == 0) prog->steps.push_back([tmA, tmB, g](cudaStream_t st) { return gemm_tc_launch(tmA, tmB, g, st); });
-                else prog->steps.push_back([g](cudaStream_t st) { return gemm_simt_launch(g, st); });
+                if (e->conv_impl == 0 && !e->gemm_v1) {
+                    void* opaque = nullptr;
+                    if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
+                    std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
+                    prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
+                } else if (e->conv_impl == 0) {
+                    CUtensorMap tmA, tmB;
+                    if (make_tmap_2d(&tmA, opA, a_inner, a_rows_u, a_stride, 64, 128)) return 1;
+                    if (make_tmap_2d(&tmB, opB, b_inner, b_rows_u, b_stride, 64, (uint32_t)BN)) return 1;
+                    prog->steps.push_back([tmA, tmB, g](cudaStream_t st) { return gemm_tc_launch(tmA, tmB, g, st); });
+                } else {
+                    prog->steps.push_back([g](cudaStream_t st) { return gemm_simt_launch(g, st); });
+                }
                 break;
             }
             case OP_IM2COL: {
@@ -302,10 +316,14 @@ static int copy_yolo_results(const YoloPostBufs& w, int batch, int max_det, floa
 }
 
 static void ufld_lut_host(float* lut) {
-    // ((float32(v) / 255.0 - mean) / std) evaluated in float64 then cast (ultrafastLaneDetectorV2.py:105-108,112)
+    // ultrafastLaneDetectorV2.py:105-108,112 under numpy promotion rules: `img / 255.0` stays float32 (python scalar is
+    // weak), `- mean` / `/ std` with python lists promote to float64, the final astype rounds once to float32.
     const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
     for (int c = 0; c < 3; ++c)
-        for (int v = 0; v < 256; ++v) lut[c * 256 + v] = (float)((((double)(float)v) / 255.0 - mean[c]) / stdv[c]);
+        for (int v = 0; v < 256; ++v) {
+            const float q = (float)v / 255.0f;
+            lut[c * 256 + v] = (float)(((double)q - mean[c]) / stdv[c]);
+        }
 }
 
 }  // namespace adas
@@ -329,6 +347,8 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->device = device; e->max_batch = max_batch; e->conv_impl = conv_impl;
     const char* ng = getenv("ADAS_B200_NO_GRAPH");
     e->use_graph = !(ng && ng[0] == '1');
+    const char* gv = getenv("ADAS_B200_GEMM");
+    e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
     if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
     e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);

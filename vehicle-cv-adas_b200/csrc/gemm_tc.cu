@@ -17,6 +17,9 @@
 // One output tile per CTA; smem is sized so two CTAs share an SM and one CTA's epilogue overlaps
 // the other's main loop.
 #include "common.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace adas {
 
@@ -150,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ================= TMA producer =================
             const uint32_t tx_bytes = A_STAGE_BYTES + p.BN * BK * 2;
             for (int kb = 0; kb < num_kb; ++kb) {
+                if ((p.dbg & 1) && kb >= stages) break;      // DEBUG: operands loaded once, MMA rate only
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
@@ -172,15 +176,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
+                if (!((p.dbg & 1) && kb >= stages)) mbar_wait(smem_u32(&full_bar[s]), ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_base + s * stage_bytes;
                 const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                if (!(p.dbg & 2)) {                          // DEBUG bit 1: skip the MMAs, TMA rate only
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ad = make_smem_desc(a_addr + k * 32);
-                    const uint64_t bd = make_smem_desc(b_addr + k * 32);
-                    umma_f16(tmem_base, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = make_smem_desc(a_addr + k * 32);
+                        const uint64_t bd = make_smem_desc(b_addr + k * 32);
+                        umma_f16(tmem_base, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                    }
                 }
                 umma_commit(smem_u32(&empty_bar[s]));   // frees the smem slot when these MMAs retire
             }
@@ -205,6 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int c = 0; c < p.BN; c += 16) {
+            if (p.dbg & 16) break;
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c, v);
             tmem_ld_wait();
@@ -230,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = act_apply(f[j], p.act);
+                    for (int j = 0; j < 16; ++j) f[j] = act_apply(f[j], (p.dbg & 8) ? 0 : p.act);
                     if (p.res != nullptr && p.res_ld > 0) {
                         // residual AFTER the activation (YOLO Bottleneck shortcut)
                         const __half* rp = p.res + (size_t)row * (size_t)p.res_ld + n;
@@ -245,6 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 4; ++j) { float2 t = __half22float2(h1[j]); f[8 + 2 * j] += t.x; f[8 + 2 * j + 1] += t.y; }
                         }
                     }
+                    if ((p.dbg & 4) && f[0] != 123456.f) continue;
                     if (p.out_f32) {
                         float* op = reinterpret_cast<float*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
                         *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
@@ -292,6 +300,411 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// =====================================================================================================
+// v2: persistent, operand-traffic-aware variant (the product path).
+//
+// Why: the first kernel moved 32-44 operand bytes-per-kMAC tiles (128 x BN) and was bound by L2->SM operand
+// traffic, not by the tensor pipe (profiles/launches_r01_v1.md).  v2 raises MACs per operand byte:
+//   * MT = 2 sub-tiles of 128 rows share every weight tile when BN <= 128 (BM = 256);
+//   * "slab" mode for 3x3 convs: one 136-row activation slab per (dy, k-block) feeds the three dx taps -- the
+//     UMMA descriptor simply starts dx rows into the slab (matrix-descriptor base offset = row phase), so the
+//     activation tile is fetched 3x instead of 9x;
+//   * persistent CTAs (one per SM) with two TMEM accumulator stages: the epilogue of tile i (8 warps) overlaps
+//     the main loop of tile i+1.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..9 epilogue.
+static constexpr int V2_THREADS = 320;
+static constexpr int SLAB_ROWS = 136;
+static constexpr int SLAB_BYTES = SLAB_ROWS * BK * 2;   // 17408 = 17 * 1024
+
+__device__ __forceinline__ uint64_t make_smem_desc_off(uint32_t smem_addr) {
+    uint64_t d = make_smem_desc(smem_addr);
+    d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;        // base offset: row phase inside the 8-row swizzle atom
+    return d;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct GemmV2 {
+    GemmParams p;
+    int MT;          // 1 or 2 sub-tiles of 128 rows per CTA tile
+    int slab;        // 1: ntaps == 9 handled as 3 dy-steps x 3 dx-taps from a shared slab
+    int a_sub_bytes; // bytes of one A sub-tile in a stage
+    int b_bytes;     // bytes of one B tile (BN rows), 1024-aligned
+    int stage_bytes;
+    int n_tiles, m_tiles, total_tiles;
+    int use_base_offset;
+};
+
+__global__ void __launch_bounds__(V2_THREADS, 1)
+gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmV2 g) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_holder;
+    __shared__ float s_bias[2][256];
+
+    const GemmParams& p = g.p;
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int taps_per_step = g.slab ? 3 : 1;
+    const int ksteps = (g.slab ? 3 : p.ntaps) * p.kpt;
+    const int BMT = BM * g.MT;
+    const int mt_cols = g.MT == 2 ? 128 : 0;      // TMEM column offset of sub-tile 1
+
+    if (warp_idx == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull_bar[s]), 1);
+            mbar_init(smem_u32(&tempty_bar[s]), V2_THREADS - 64);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp_idx == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            const uint32_t tx_bytes = (uint32_t)(g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + taps_per_step * p.BN * BK * 2);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+                const int n0 = (t % g.n_tiles) * p.BN;
+                const int m0 = (t / g.n_tiles) * BMT;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, tx_bytes);
+                    const int grp = ks / p.kpt;            // dy (slab) or tap (plain)
+                    const int kc = ks - grp * p.kpt;
+                    const uint32_t a_dst = smem_base + s * g.stage_bytes;
+                    const uint32_t b_dst = a_dst + g.MT * g.a_sub_bytes;
+                    if (g.slab) {
+                        const int r0 = m0 + (grp - 1) * p.Wp - 1;
+                        for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
+                        for (int dx = 0; dx < 3; ++dx)
+                            tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
+                    } else {
+                        int shift = 0;
+                        if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
+                        for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
+                        tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0, tile_it = 0;
+            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tile_it) {
+                const int as = tile_it & 1;
+                mbar_wait(smem_u32(&tempty_bar[as]), ((tile_it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
+                tcgen05_fence_after();
+                const uint32_t d_base = tmem_base + (uint32_t)(as * 256);
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_base + s * g.stage_bytes;
+                    const uint32_t b_addr = a_addr + g.MT * g.a_sub_bytes;
+                    for (int dx = 0; dx < taps_per_step; ++dx) {
+                        if (p.dbg & 2) break;
+                        for (int mt = 0; mt < g.MT; ++mt) {
+                            const uint32_t a_sub = a_addr + mt * g.a_sub_bytes + (g.slab ? dx * 128 : 0);
+                            const uint32_t b_sub = b_addr + dx * g.b_bytes;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t ad = g.use_base_offset ? make_smem_desc_off(a_sub + k * 32) : make_smem_desc(a_sub + k * 32);
+                                const uint64_t bd = make_smem_desc(b_sub + k * 32);
+                                umma_f16(d_base + (uint32_t)(mt * mt_cols), ad, bd, idesc, (uint32_t)((ks | dx | k) != 0));
+                            }
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                }
+                umma_commit(smem_u32(&tfull_bar[as]));
+            }
+        }
+    } else {
+        // ================= epilogue (8 warps) =================
+        // Each warp owns TMEM lane quarter q; the two warps sharing a quarter alternate 32-column batches.
+        // Per batch: two tcgen05.ld.x16 are issued, the bias (smem broadcast) and residual (global) operands are
+        // fetched while they are in flight, then one wait, the math, and 16-byte stores of the thread's row.
+        const int q = warp_idx & 3;
+        const int half = (warp_idx - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        uint32_t tile_it = 0;
+        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tile_it) {
+            const int as = tile_it & 1;
+            const int n0 = (t % g.n_tiles) * p.BN;
+            const int m0 = (t / g.n_tiles) * BMT;
+            if (!p.transposed) {
+                for (int j = et; j < p.BN; j += V2_THREADS - 64)
+                    s_bias[as][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(smem_u32(&tfull_bar[as]), (tile_it >> 1) & 1u);
+            tcgen05_fence_after();
+            for (int mt = 0; mt < g.MT; ++mt) {
+                const int row = m0 + mt * BM + q * 32 + lane;
+                bool row_ok = row < p.M;
+                if (p.mask_H > 0 && row_ok) {
+                    const int Wp = p.mask_W + 2;
+                    const int img = (p.mask_H + 2) * Wp;
+                    const int pp = row % img;
+                    const int yy = pp / Wp;
+                    const int xx = pp - yy * Wp;
+                    row_ok = (yy >= 1) && (yy <= p.mask_H) && (xx >= 1) && (xx <= p.mask_W);
+                }
+                float row_bias = 0.f;
+                if (p.transposed && p.bias != nullptr && row < p.M) row_bias = p.bias[row];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + mt * mt_cols);
+                const size_t res_ld = (size_t)(p.res_ld < 0 ? -p.res_ld : p.res_ld);
+                for (int c = half * 32; c < p.BN; c += 64) {
+                    if (p.dbg & 16) break;
+                    const bool two = (c + 16) < p.BN;          // BN is a multiple of 16: a batch is 32 or 16 columns
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(taddr + (uint32_t)c, v0);
+                    if (two) tmem_ld16(taddr + (uint32_t)(c + 16), v1);
+                    const int n = n0 + c;
+                    const int ncols = min(two ? 32 : 16, p.N - n);     // valid columns in this batch (multiple of 8, may be <= 0)
+                    // operands fetched under the TMEM load latency
+                    uint4 rr[4];
+                    const bool has_res = (p.res != nullptr) && row_ok && !p.transposed;
+                    if (has_res) {
+                        const __half* rp = p.res + (size_t)row * res_ld + n;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k * 8 < ncols) rr[k] = *reinterpret_cast<const uint4*>(rp + k * 8);
+                    }
+                    tmem_ld_wait();
+                    if (!p.transposed) {
+                        if (row_ok && ncols > 0) {
+                            float f[32];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v0[j]) + s_bias[as][c + j];
+                            if (two) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) f[16 + j] = __uint_as_float(v1[j]) + s_bias[as][c + 16 + j];
+                            }
+                            if (has_res && p.res_ld < 0) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k * 8 < ncols) {
+                                        const __half2* h = reinterpret_cast<const __half2*>(&rr[k]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) { float2 tt = __half22float2(h[j]); f[k * 8 + 2 * j] += tt.x; f[k * 8 + 2 * j + 1] += tt.y; }
+                                    }
+                            }
+                            const int act = (p.dbg & 8) ? 0 : p.act;
+                            if (act == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+                            } else if (act == 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                            }
+                            if (has_res && p.res_ld > 0) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k * 8 < ncols) {
+                                        const __half2* h = reinterpret_cast<const __half2*>(&rr[k]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) { float2 tt = __half22float2(h[j]); f[k * 8 + 2 * j] += tt.x; f[k * 8 + 2 * j + 1] += tt.y; }
+                                    }
+                            }
+                            if ((p.dbg & 4) && f[0] != 123456.f) continue;
+                            if (p.out_f32) {
+                                float* op = reinterpret_cast<float*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if (k * 4 < ncols) *reinterpret_cast<float4*>(op + k * 4) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                            } else {
+                                __half* op = reinterpret_cast<__half*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k * 8 < ncols) {
+                                        uint4 o;
+                                        __half2* qh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) qh[j] = __floats2half2_rn(f[k * 8 + 2 * j], f[k * 8 + 2 * j + 1]);
+                                        *reinterpret_cast<uint4*>(op + k * 8) = o;
+                                    }
+                            }
+                        }
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = n + j;
+                            if (col < p.N && (j < 16 || two)) {
+                                const float x = act_apply(__uint_as_float(j < 16 ? v0[j & 15] : v1[j & 15]) + row_bias, p.act);
+                                if (p.out_f32) reinterpret_cast<float*>(p.out)[(size_t)col * (size_t)p.out_ld + row] = x;
+                                else reinterpret_cast<__half*>(p.out)[(size_t)col * (size_t)p.out_ld + row] = __float2half_rn(x);
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[as]));      // this thread is done reading accumulator stage `as`
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static int g_num_sms = 0;
+
+int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
+    g->p = p;
+    g->MT = (p.BN <= 128) ? 2 : 1;
+    if (p.mt_hint == 1) g->MT = 1;
+    const int b_bytes = ((p.BN * BK * 2) + 1023) & ~1023;
+    g->b_bytes = b_bytes;
+    const int budget = 218 * 1024;
+    g->slab = 0;
+    if (p.ntaps == 9) {
+        const int slab_stage = g->MT * SLAB_BYTES + 3 * b_bytes;
+        if (2 * slab_stage <= budget) g->slab = 1;
+    }
+    g->a_sub_bytes = g->slab ? SLAB_BYTES : A_STAGE_BYTES;
+    g->stage_bytes = g->MT * g->a_sub_bytes + (g->slab ? 3 : 1) * b_bytes;
+    int stages = budget / g->stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return 1;
+    g->p.stages = stages;
+    const int BMT = BM * g->MT;
+    g->n_tiles = (p.N + p.BN - 1) / p.BN;
+    g->m_tiles = (p.M + BMT - 1) / BMT;
+    g->total_tiles = g->n_tiles * g->m_tiles;
+    const char* bo = getenv("ADAS_B200_BASEOFF");
+    g->use_base_offset = (bo && bo[0] == '1');   // measured on B200: the swizzle phase follows the absolute smem address, the field stays 0
+    static int dbg = -1;
+    if (dbg < 0) { const char* d = getenv("ADAS_B200_DBG"); dbg = d ? atoi(d) : 0; }
+    g->p.dbg = dbg;
+    const char* ns = getenv("ADAS_B200_NOSLAB");
+    if (ns && ns[0] == '1' && g->slab) {
+        g->slab = 0;
+        g->a_sub_bytes = A_STAGE_BYTES;
+        g->stage_bytes = g->MT * g->a_sub_bytes + b_bytes;
+        stages = budget / g->stage_bytes;
+        if (stages > 8) stages = 8;
+        g->p.stages = stages;
+    }
+    return 0;
+}
+
+int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmV2& g, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        int dev = 0;
+        ADAS_CUDA(cudaGetDevice(&dev));
+        ADAS_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr = true;
+    }
+    const int smem = g.p.stages * g.stage_bytes + 1024;
+    int grid = g.total_tiles < g_num_sms ? g.total_tiles : g_num_sms;
+    gemm_tc_v2_kernel<<<grid, V2_THREADS, smem, st>>>(tmA, tmB, g);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// Per-layer tile choice.  Measured on B200 (profiles/r01_gemm_analysis.md): one SM ingests ~32 operand bytes per
+// clock from L2 while its tensor pipe retires 4096 MACs per clock, so a tile is modelled by max(operand bytes / 32,
+// MMA clocks, epilogue clocks) and layers are charged whole waves of 148 persistent CTAs.
+void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out) {
+    const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+    double best = 1e30;
+    int bBN = 0, bMT = 0;
+    const int kpt = (Kc + 63) / 64;
+    for (int ci = 0; ci < 10; ++ci) {
+        int BN = cand[ci];
+        if (BN > N) { if (ci + 1 < 10 && cand[ci + 1] >= N) continue; BN = (N + 15) / 16 * 16; }
+        if (BN > 256) continue;
+        const int n_tiles = (N + BN - 1) / BN;
+        if ((double)n_tiles * BN > 1.35 * N) continue;          // too much padded-N work
+        for (int mt = 1; mt <= 2; ++mt) {
+            if (mt == 2 && BN > 128) continue;
+            GemmParams p;
+            memset(&p, 0, sizeof(p));
+            p.M = M; p.N = N; p.Kc = Kc; p.ntaps = ntaps; p.kpt = kpt; p.BN = BN; p.mt_hint = mt == 1 ? 1 : 0;
+            GemmV2 g;
+            if (gemm_tc_v2_config(p, &g)) continue;
+            const double tiles = (double)g.total_tiles;
+            const double ksteps = (g.slab ? 3.0 : (double)ntaps) * kpt;
+            const double bytes = ksteps * (g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + (g.slab ? 3 : 1) * BN * 128.0);
+            const double mma = (double)g.MT * ntaps * kpt * 2.0 * BN;
+            const double epi = (double)g.MT * 128.0 * BN * 0.55;
+            const double per_tile = fmax(fmax(bytes / 32.0, mma), epi) + 600.0;
+            const double waves = ceil(tiles / 148.0);
+            // a CTA's first tile cannot overlap its epilogue with anything: charge it once per launch
+            const double t = waves * per_tile + epi * 0.5 + 2500.0;
+            if (t < best) { best = t; bBN = BN; bMT = mt; }
+        }
+    }
+    if (bBN == 0) { bBN = N <= 256 ? (N + 15) / 16 * 16 : 256; bMT = bBN <= 128 ? 2 : 1; }
+    *BN_out = bBN;
+    *mt_hint_out = bMT == 1 ? 1 : 0;
+}
+
+struct GemmV2Launch {
+    CUtensorMap tmA, tmB;
+    GemmV2 g;
+};
+
+int gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
+                       const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque) {
+    ADAS_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "gemm_tc_v2: bad BN %d", p.BN);
+    ADAS_CHECK(p.N % 8 == 0 || p.transposed, "gemm_tc_v2: N %d must be a multiple of 8", p.N);
+    GemmV2Launch* L = new GemmV2Launch();
+    if (gemm_tc_v2_config(p, &L->g)) { delete L; ADAS_CHECK(false, "gemm_tc_v2: tile does not fit in shared memory (BN %d)", p.BN); }
+    const uint32_t a_box_rows = L->g.slab ? SLAB_ROWS : BM;
+    if (make_tmap_2d(&L->tmA, a_base, a_inner, a_rows, a_stride_bytes, 64, a_box_rows) ||
+        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)p.BN)) {
+        delete L;
+        return 1;
+    }
+    *opaque = L;
+    return 0;
+}
+
+int gemm_tc_v2_run(void* opaque, cudaStream_t st) {
+    GemmV2Launch* L = static_cast<GemmV2Launch*>(opaque);
+    return gemm_tc_v2_launch(L->tmA, L->tmB, L->g, st);
+}
+
+void gemm_tc_v2_free(void* opaque) { delete static_cast<GemmV2Launch*>(opaque); }
+
 int gemm_tc_smem_bytes(int BN, int stages) {
     const int b_stage = ((BN * BK * 2) + 1023) & ~1023;
     return stages * (A_STAGE_BYTES + b_stage) + 1024;
@@ -308,7 +721,11 @@ int gemm_tc_pick_stages(int BN, int num_kb) {
     return s;
 }
 
-int gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+int gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, cudaStream_t st) {
+    GemmParams p = p_in;
+    static int dbg = -1;
+    if (dbg < 0) { const char* d = getenv("ADAS_B200_DBG"); dbg = d ? atoi(d) : 0; }
+    p.dbg = dbg;
     ADAS_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "gemm_tc: bad BN %d", p.BN);
     ADAS_CHECK(p.N % 8 == 0 || p.transposed, "gemm_tc: N %d must be a multiple of 8", p.N);
     ADAS_CHECK(p.stages >= 2 && p.stages <= 8, "gemm_tc: bad stage count %d", p.stages);

@@ -117,32 +117,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------------------
-class B200Pipeline:
-    def __init__(self, plans, device: int, batch: int):
-        from adas_b200 import _capi
-        from adas_b200.ObjectTracker import BYTETracker
-        self.capi = _capi
-        self.batch = batch
-        self.yolo = _capi.Engine(plans["yolov8"][0], device, max_batch=batch)
-        self.ufld = _capi.Engine(plans["ufldv2"][0], device, max_batch=batch)
-        self.tracker = BYTETracker(names=[], device=device)
-        self.tracker.reset()
-        self.last = None
-
-    def step(self, frames, on_device: bool, shape=None):
-        y = self.yolo.yolo_detect(frames, BOX_SCORE, NMS_IOU, MAX_DET, on_device=on_device, shape=shape)
-        u = self.ufld.ufld_detect(frames, on_device=on_device, shape=shape)
-        boxes, scores, cls, _, counts, _ = y
-        tracks = []
-        for b in range(self.batch):
-            n = int(counts[b])
-            bx = boxes[b, :n]
-            xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(int) if n else np.zeros((0, 4), int)
-            tracks.append(self.tracker.update(xyxy, scores[b, :n], cls[b, :n], None))
-        self.last = (y, u, tracks)
-        return y, u, tracks
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -162,7 +136,8 @@ def run_b200(args):
         dist.barrier()
     if rank != 0:
         plans = build_plans()
-    pipe = B200Pipeline(plans, local, B)
+    from adas_b200.pipeline import AdasPipeline
+    pipe = AdasPipeline(plans["yolov8"][0], plans["ufldv2"][0], device=local, batch=B, box_score=BOX_SCORE, box_nms_iou=NMS_IOU, max_det=MAX_DET)
 
     # one stream per rank; frames differ per step (pool larger than L2: 24 batches x 22 MB = 530 MB >> 126 MB)
     pool_batches = 24
@@ -176,12 +151,13 @@ def run_b200(args):
     gather_buf = torch.zeros((B, MAX_DET, 7), dtype=torch.float32, device=f"cuda:{local}")
     gathered = [torch.zeros_like(gather_buf) for _ in range(world)] if world > 1 else None
 
-    def gather(y):
-        if world == 1:
+    def gather(r):
+        if world == 1 or r is None:
             return
-        boxes, scores, cls, _, counts, _ = y
         rec = np.zeros((B, MAX_DET, 7), np.float32)
-        rec[..., :4], rec[..., 4], rec[..., 5] = boxes, scores, cls
+        rec[..., :4], rec[..., 4], rec[..., 5] = r.boxes, r.scores, r.class_ids
+        for b, tr in enumerate(r.tracks or []):
+            rec[b, :min(len(tr), MAX_DET), 6] = [t["track_id"] for t in tr][:MAX_DET]
         gather_buf.copy_(torch.from_numpy(rec), non_blocking=True)
         dist.all_gather(gathered, gather_buf)
 
@@ -191,30 +167,48 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream()
+    stage = [torch.empty((B, FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=f"cuda:{local}") for _ in range(2)]
+    copy_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(slot, j):            # pinned host -> device staging on a side stream (overlaps the previous batch's compute)
+        with torch.cuda.stream(copy_stream):
+            stage[slot].copy_(host_pool[j], non_blocking=True)
+            copy_ev[slot].record(copy_stream)
+
+    def run_steps(n, first, on_device):
+        if not on_device:
+            upload(0, first % pool_batches)
+        for i in range(n):
+            j = (first + i) % pool_batches
+            if on_device:
+                ptr = dev_pool[j].data_ptr()
+            else:
+                copy_ev[i % 2].synchronize()
+                if i + 1 < n:
+                    upload((i + 1) % 2, (first + i + 1) % pool_batches)
+                ptr = stage[i % 2].data_ptr()
+            gather(pipe.step_pipelined(ptr, True, (B, FRAME_H, FRAME_W)))
+        gather(pipe.flush())
+
     def timed(on_device: bool):
-        for i in range(Wm):
-            fr = dev_pool[i % pool_batches] if on_device else hp[i % pool_batches]
-            y, _, _ = pipe.step(fr.data_ptr() if on_device else fr, on_device, (B, FRAME_H, FRAME_W))
-            gather(y)
+        run_steps(Wm, 0, on_device)
         barrier()
         n0 = _capi.launch_count()
         sampler = ClockSampler(local)
         sampler.start()
         pipe.yolo.event_record(0)
         t0 = time.perf_counter()
-        for i in range(K):
-            j = (Wm + i) % pool_batches
-            fr = dev_pool[j] if on_device else hp[j]
-            y, _, _ = pipe.step(fr.data_ptr() if on_device else fr, on_device, (B, FRAME_H, FRAME_W))
-            gather(y)
+        run_steps(K, Wm, on_device)
         pipe.ufld.event_record(1)
+        pipe.yolo.event_record(1)
         torch.cuda.synchronize()
-        ms_dev = pipe.yolo.elapsed_ms(0, pipe.ufld, 1)
+        ms_dev = max(pipe.yolo.elapsed_ms(0, pipe.ufld, 1), pipe.yolo.elapsed_ms(0, pipe.yolo, 1))
         ms_wall = (time.perf_counter() - t0) * 1e3
         clocks = sampler.stop()
         launches = _capi.launch_count() - n0
         barrier()
-        # the tracker runs on the host after the last device event: take the larger of the two clocks
+        # the tracker of the last batch runs on the host after the last device event: take the larger of the two clocks
         ms = max(ms_dev, ms_wall)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -257,9 +251,10 @@ def run_b200(args):
                        "global_batch": world * B, "parallelism": f"dp{world} (one stream per GPU, NCCL all_gather of detection records)",
                        "weights": "seeded synthetic (He-normal, BN folded), fp16 operands, fp32 accumulate",
                        "l2": f"inputs rotate through a {pool_batches}-batch pool ({pool_batches * B * FRAME_H * FRAME_W * 3 / 1e6:.0f} MB > 126 MB L2)"},
-            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": 2 * B * FRAME_H * FRAME_W * 3,
+            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_H * FRAME_W * 3,
                     "d2h_bytes_per_step": int(B * (MAX_DET * (16 + 4 + 4 + 4) + 8) + B * (4 * 81 * 2 * 4 + 16 + 4)),
-                    "ms_per_step": round(ms_e2e / K, 4), "note": "each engine uploads the batch itself (YOLO and UFLD handles are independent)"},
+                    "ms_per_step": round(ms_e2e / K, 4),
+                    "note": "adas_b200.pipeline.AdasPipeline.step_pipelined: pinned host batch -> device staging (side stream), both detectors, tracker; results on the host every step"},
             "gpu_launches": int(launches),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": round(achieved, 1), "peak": peak,
@@ -286,7 +281,7 @@ class CpuReferencePath:
         import torch
         from oracle import nets, post, track
         self.torch, self.post = torch, post
-        torch.set_num_threads(os.cpu_count() or 1)
+        self.threads = pick_cpu_threads()
         self.yolo = nets.build("yolov8", plans["yolov8"][1], scale="l")
         self.ufld = nets.build("ufldv2", plans["ufldv2"][1], backbone="34")
         self.trk = track.Tracker()
@@ -308,6 +303,34 @@ class CpuReferencePath:
         return det, lanes
 
 
+_CPU_THREADS = None
+
+
+def pick_cpu_threads() -> int:
+    """All the host threads torch can USE: oneDNN convolutions stop scaling (and collapse under oversubscription) well
+    before 100+ logical CPUs, so time one conv stack at a few thread counts up to the affinity mask and keep the fastest."""
+    global _CPU_THREADS
+    import torch
+    if _CPU_THREADS is None:
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        net = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 3, padding=1), torch.nn.SiLU(), torch.nn.Conv2d(128, 128, 3, padding=1)).eval()
+        x = torch.randn(1, 64, 160, 160)
+        best, best_t = 1, 1e9
+        for n in sorted({c for c in (4, 8, 16, 32, 64, avail) if c <= avail}):
+            torch.set_num_threads(n)
+            with torch.no_grad():
+                net(x)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    net(x)
+                dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = n, dt
+        _CPU_THREADS = best
+    torch.set_num_threads(_CPU_THREADS)
+    return _CPU_THREADS
+
+
 def cpu_baseline_sample(plans, frames: int = 8):
     path = CpuReferencePath(plans)
     imgs = synth_stream(1000, frames + 1)
@@ -316,7 +339,7 @@ def cpu_baseline_sample(plans, frames: int = 8):
     for i in range(frames):
         path.frame(imgs[1 + i])
     dt = time.perf_counter() - t0
-    return {"value": round(frames / dt, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": round(frames / dt, 3), "unit": "frames/s", "cores": path.threads, "kind": "port",
             "sample": f"{frames} consecutive 1280x720 frames, batch 1 (the reference's only mode), oracle port: reference pre/post/tracker "
                       "semantics in numpy + torch-CPU fp32 nets (onnxruntime absent -> torch-CPU substitutes ORT-CPU)"}
 
@@ -350,7 +373,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "YOLOv8l 640x640 + UFLDv2-CULane-ResNet34 320x1600 + ByteTrack, 1280x720 synthetic stream (CPU, bounded sample)",
                    "frames_per_step": per_step},
-        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": path.threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 

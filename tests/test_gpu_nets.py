@@ -19,7 +19,7 @@ from gpu_util import cached_plan
 from oracle import nets, post
 
 pytestmark = pytest.mark.gpu
-torch.set_num_threads(max(1, os.cpu_count() or 1))
+torch.set_num_threads(min(16, max(1, os.cpu_count() or 1)))   # oneDNN collapses under 100+ threads
 
 
 def _blob(frames):

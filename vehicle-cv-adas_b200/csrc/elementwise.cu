@@ -44,9 +44,47 @@ __global__ void im2col_kernel(const __half* __restrict__ in, int in_ld, int in_c
     }
 }
 
+// 16-byte variant (Cin % 8 == 0): one thread moves 8 channels of one tap; consecutive threads cover consecutive
+// 16-byte chunks of the output row, so both the gather reads (Cin*2-byte runs) and the writes are full sectors.
+__global__ void im2col8_kernel(const __half* __restrict__ in, int in_ld, int in_coff, int B, int H, int W, int Cin,
+                               int kh, int kw, int stride, int pad, int Ho, int Wo, __half* __restrict__ out, int Kpad) {
+    const int c8 = Cin >> 3;
+    const int per_px = kh * kw * c8;
+    const long long total = (long long)B * Ho * Wo * per_px;
+    const int Hp = H + 2, Wp = W + 2, Hop = Ho + 2, Wop = Wo + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % per_px);
+        long long t = i / per_px;
+        const int cg = r % c8;
+        const int tap = r / c8;
+        const int kx = tap % kw, ky = tap / kw;
+        const int xo = (int)(t % Wo); t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int yi = yo * stride - pad + ky;
+        const int xi = xo * stride - pad + kx;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+            const size_t rr = ((size_t)b * Hp + (yi + 1)) * Wp + (xi + 1);
+            v = *reinterpret_cast<const uint4*>(in + rr * in_ld + in_coff + cg * 8);
+        }
+        const size_t orow = ((size_t)b * Hop + (yo + 1)) * Wop + (xo + 1);
+        *reinterpret_cast<uint4*>(out + orow * Kpad + (tap * Cin + cg * 8)) = v;
+    }
+}
+
 int launch_im2col(const __half* in, int in_ld, int in_coff, int B, int H, int W, int Cin, int kh, int kw, int stride,
                   int pad, int Ho, int Wo, __half* out, int Kpad, cudaStream_t st) {
     ADAS_CHECK(Cin % 4 == 0 && in_ld % 4 == 0 && in_coff % 4 == 0 && Kpad % 4 == 0, "im2col: channel alignment");
+    if (Cin % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && Kpad % 8 == 0) {
+        const long long total8 = (long long)B * Ho * Wo * kh * kw * (Cin / 8);
+        int blocks8 = grid_for(total8, 256);
+        if (blocks8 > 148 * 16) blocks8 = 148 * 16;
+        im2col8_kernel<<<blocks8, 256, 0, st>>>(in, in_ld, in_coff, B, H, W, Cin, kh, kw, stride, pad, Ho, Wo, out, Kpad);
+        count_launch();
+        ADAS_CUDA(cudaGetLastError());
+        return 0;
+    }
     const long long total = (long long)B * Ho * Wo * kh * kw * (Cin / 4);
     int blocks = grid_for(total, 256);
     if (blocks > 148 * 32) blocks = 148 * 32;

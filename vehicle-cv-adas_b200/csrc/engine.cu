@@ -55,6 +55,7 @@ struct adas_engine {
     int conv_impl = 0;
     bool use_graph = true;
     bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
+    bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
     cudaStream_t stream = nullptr;
     PlanHeader hdr;
     std::vector<PlanBuffer> bufs;
@@ -158,7 +159,34 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
                 if (e->conv_impl == 0 && !e->gemm_v1) {
                     void* opaque = nullptr;
-                    if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
+                    if (e->autotune && !transposed && p[15] <= 0) {
+                        // measure the modelled top candidates on the device once per (op, batch); every candidate accumulates in the
+                        // same K order, so the choice never changes results
+                        int cBN[6], cMT[6];
+                        const int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 6, cBN, cMT);
+                        float best_ms = 1e30f;
+                        cudaEvent_t ev0, ev1;
+                        ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1));
+                        for (int ci = 0; ci < nc; ++ci) {
+                            GemmParams gc = g;
+                            gc.BN = cBN[ci]; gc.mt_hint = cMT[ci];
+                            void* cand = nullptr;
+                            if (gemm_tc_v2_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &cand)) continue;
+                            int rc = gemm_tc_v2_run(cand, e->stream);
+                            if (!rc) {
+                                cudaEventRecord(ev0, e->stream);
+                                for (int r = 0; r < 3 && !rc; ++r) rc = gemm_tc_v2_run(cand, e->stream);
+                                cudaEventRecord(ev1, e->stream);
+                                if (cudaEventSynchronize(ev1) != cudaSuccess) rc = 1;
+                            }
+                            float ms = 1e30f;
+                            if (!rc) cudaEventElapsedTime(&ms, ev0, ev1);
+                            if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_tc_v2_free(opaque); opaque = cand; }
+                            else gemm_tc_v2_free(cand);
+                        }
+                        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+                        ADAS_CHECK(opaque != nullptr, "op %zu: no GEMM tile configuration could be launched", oi);
+                    } else if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
                     std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
                 } else if (e->conv_impl == 0) {
@@ -349,6 +377,8 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->use_graph = !(ng && ng[0] == '1');
     const char* gv = getenv("ADAS_B200_GEMM");
     e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
+    const char* at = getenv("ADAS_B200_AUTOTUNE");
+    e->autotune = !(at && at[0] == '0');
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
     if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
     e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);

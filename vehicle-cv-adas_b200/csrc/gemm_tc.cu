@@ -394,8 +394,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     mbar_expect_tx(fb, tx_bytes);
-                    const int grp = ks / p.kpt;            // dy (slab) or tap (plain)
-                    const int kc = ks - grp * p.kpt;
+                    // K order is (dy, k-block, dx) in BOTH modes so every output element accumulates in the same order
+                    // whatever tile shape the autotuner picks (bit-identical results across batch sizes).
+                    int grp, kc;
+                    if (g.slab || p.ntaps != 9) { grp = ks / p.kpt; kc = ks - grp * p.kpt; }
+                    else { const int dy = ks / (3 * p.kpt); const int r = ks - dy * 3 * p.kpt; kc = r / 3; grp = dy * 3 + (r - kc * 3); }
                     const uint32_t a_dst = smem_base + s * g.stage_bytes;
                     const uint32_t b_dst = a_dst + g.MT * g.a_sub_bytes;
                     if (g.slab) {
@@ -642,10 +645,10 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 // Per-layer tile choice.  Measured on B200 (profiles/r01_gemm_analysis.md): one SM ingests ~32 operand bytes per
 // clock from L2 while its tensor pipe retires 4096 MACs per clock, so a tile is modelled by max(operand bytes / 32,
 // MMA clocks, epilogue clocks) and layers are charged whole waves of 148 persistent CTAs.
-void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out) {
+int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out) {
     const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
-    double best = 1e30;
-    int bBN = 0, bMT = 0;
+    struct C { double t; int BN, mt; } list[24];
+    int n = 0;
     const int kpt = (Kc + 63) / 64;
     for (int ci = 0; ci < 10; ++ci) {
         int BN = cand[ci];
@@ -653,6 +656,9 @@ void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hin
         if (BN > 256) continue;
         const int n_tiles = (N + BN - 1) / BN;
         if ((double)n_tiles * BN > 1.35 * N) continue;          // too much padded-N work
+        bool dup = false;
+        for (int k = 0; k < n; ++k) dup = dup || (list[k].BN == BN);
+        if (dup) continue;
         for (int mt = 1; mt <= 2; ++mt) {
             if (mt == 2 && BN > 128) continue;
             GemmParams p;
@@ -667,14 +673,20 @@ void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hin
             const double epi = (double)g.MT * 128.0 * BN * 0.55;
             const double per_tile = fmax(fmax(bytes / 32.0, mma), epi) + 600.0;
             const double waves = ceil(tiles / 148.0);
-            // a CTA's first tile cannot overlap its epilogue with anything: charge it once per launch
             const double t = waves * per_tile + epi * 0.5 + 2500.0;
-            if (t < best) { best = t; bBN = BN; bMT = mt; }
+            if (n < 24) { list[n].t = t; list[n].BN = BN; list[n].mt = mt; ++n; }
         }
     }
-    if (bBN == 0) { bBN = N <= 256 ? (N + 15) / 16 * 16 : 256; bMT = bBN <= 128 ? 2 : 1; }
-    *BN_out = bBN;
-    *mt_hint_out = bMT == 1 ? 1 : 0;
+    // insertion sort by modelled time
+    for (int i = 1; i < n; ++i) { C c = list[i]; int j = i - 1; while (j >= 0 && list[j].t > c.t) { list[j + 1] = list[j]; --j; } list[j + 1] = c; }
+    if (n == 0) { list[0].BN = N <= 256 ? (N + 15) / 16 * 16 : 256; list[0].mt = list[0].BN <= 128 ? 2 : 1; n = 1; }
+    if (n > max_out) n = max_out;
+    for (int i = 0; i < n; ++i) { BN_out[i] = list[i].BN; mt_hint_out[i] = list[i].mt == 1 ? 1 : 0; }
+    return n;
+}
+
+void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out) {
+    gemm_tc_v2_candidates(M, N, Kc, ntaps, 1, BN_out, mt_hint_out);
 }
 
 struct GemmV2Launch {

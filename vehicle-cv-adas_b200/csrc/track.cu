@@ -111,6 +111,7 @@ __global__ void lap_kernel(const double* __restrict__ cost, const int64_t* __res
                 const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
                 if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
             }
+            if (bj == 0x7fffffff) break;      // no finite candidate (NaN costs): leave the row unmatched instead of spinning
             const double delta = bd;
             const int j1 = bj;
             for (int j = lane; j <= m; j += 32) {
@@ -122,7 +123,7 @@ __global__ void lap_kernel(const double* __restrict__ cost, const int64_t* __res
             if (p[j0] == 0) break;
         }
         // augment along the alternating path
-        if (lane == 0) {
+        if (lane == 0 && p[j0] == 0) {
             while (j0 != 0) {
                 const int j1 = way[j0];
                 p[j0] = p[j1];

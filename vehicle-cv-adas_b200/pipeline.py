@@ -1,0 +1,86 @@
+"""pipeline.py -- the per-frame loop of the reference's demo.py (261-316) as a batched, overlapped stream runner.
+
+demo.py does, per frame and strictly in sequence: `objectDetector.DetectFrame` (269) -> `objectTracker.update` (272-277)
+-> `laneDetector.DetectFrame` (280) -> analytics/drawing.  Here one step takes a batch of consecutive frames of one
+stream:  the object and lane networks run concurrently on their own engine handles / CUDA streams (two worker threads;
+the ctypes calls release the GIL), while the host thread runs the ByteTrack updates of the PREVIOUS batch -- the tracker
+is sequential in time per stream, so it pipelines one batch behind the detectors.  Per-frame results are
+identical to calling the three detectors frame by frame.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional
+
+import numpy as np
+
+from . import _capi
+from .ObjectTracker import BYTETracker
+
+
+class StepResult:
+    __slots__ = ("boxes", "scores", "class_ids", "counts", "lane_pts", "lane_npts", "lane_status", "tracks")
+
+    def __init__(self, y, u):
+        self.boxes, self.scores, self.class_ids, _, self.counts, _ = y
+        self.lane_pts, self.lane_npts, self.lane_status, _ = u
+        self.tracks: Optional[List[list]] = None
+
+
+class AdasPipeline:
+    def __init__(self, yolo_plan: str, ufld_plan: str, device: int = 0, batch: int = 8, box_score: float = 0.4, box_nms_iou: float = 0.45,
+                 max_det: int = 300, class_names: Optional[List[str]] = None):
+        self.batch, self.box_score, self.box_nms_iou, self.max_det = batch, box_score, box_nms_iou, max_det
+        self.yolo = _capi.Engine(yolo_plan, device, max_batch=batch)
+        self.ufld = _capi.Engine(ufld_plan, device, max_batch=batch)
+        self.tracker = BYTETracker(names=class_names or [], device=device)
+        self.tracker.reset()
+        self.class_names = class_names
+        self._pool = ThreadPoolExecutor(max_workers=2)
+        self._pending: Optional[StepResult] = None
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        self.yolo.close()
+        self.ufld.close()
+
+    # -- stages -------------------------------------------------------------------------------------------
+    def _detect(self, frames, on_device: bool, shape):
+        fy = self._pool.submit(self.yolo.yolo_detect, frames, self.box_score, self.box_nms_iou, self.max_det, on_device, shape)
+        fu = self._pool.submit(self.ufld.ufld_detect, frames, on_device, shape)
+        return fy, fu
+
+    def _track(self, r: StepResult) -> None:
+        out = []
+        for b in range(len(r.counts)):
+            n = int(r.counts[b])
+            bx = r.boxes[b, :n]
+            # demo.py:272-275 feeds RectInfo.tolist("xyxy") -> ints, and the label as class id
+            xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(int) if n else np.zeros((0, 4), int)
+            ids = r.class_ids[b, :n] if self.class_names is None else [self.class_names[c] for c in r.class_ids[b, :n]]
+            out.append(self.tracker.update(xyxy, r.scores[b, :n], ids, None))
+        r.tracks = out
+
+    # -- public ---------------------------------------------------------------------------------------------
+    def step(self, frames, on_device: bool = False, shape=None) -> StepResult:
+        """Synchronous: detectors (concurrently), then the tracker for this batch."""
+        fy, fu = self._detect(frames, on_device, shape)
+        r = StepResult(fy.result(), fu.result())
+        self._track(r)
+        return r
+
+    def step_pipelined(self, frames, on_device: bool = False, shape=None) -> Optional[StepResult]:
+        """Submit this batch to the detectors and, while they run, track the previous batch.  Returns the previous batch's
+        complete result (None on the first call); call flush() after the last batch."""
+        fy, fu = self._detect(frames, on_device, shape)
+        done = self._pending
+        if done is not None:
+            self._track(done)
+        self._pending = StepResult(fy.result(), fu.result())
+        return done
+
+    def flush(self) -> Optional[StepResult]:
+        done, self._pending = self._pending, None
+        if done is not None:
+            self._track(done)
+        return done

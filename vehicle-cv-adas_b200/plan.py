@@ -129,8 +129,8 @@ class Weights:
 # heads give logits ~ N(0, 0.07^2), i.e. every score ~0.5.  The profiles widen the final 1x1 head convs and shift
 # their biases so that O(100) of the 8400 / 25200 anchors clear box_score = 0.4 and the DFL boxes vary in size.
 SYNTH_PROFILES = {
-    "yolov8": {"gains": [(r"model\.22\.cv3\.\d\.2\.weight", 22.0), (r"model\.22\.cv2\.\d\.2\.weight", 25.0)],
-               "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -4.55)]},
+    "yolov8": {"gains": [(r"model\.22\.cv3\.\d\.2\.weight", 66.0), (r"model\.22\.cv2\.\d\.2\.weight", 25.0)],
+               "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -12.84)]},
     "yolov5": {"gains": [(r"model\.24\.m\.\d\.weight", 30.0)],
                "fill": [(r"model\.24\.m\.\d\.bias", -4.3)]},
     "ufldv2": {},

@@ -112,6 +112,14 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
                      int H, int W, int32_t* pts, int32_t* npts, uint8_t* status,
                      double* coords_f);
 
+/* adas_detect_pair: one call = adas_yolo_detect followed by adas_ufld_detect on the same frames (demo.py:269,280 run
+ * both detectors on every frame).  Exists so a host thread that pipelines the tracker needs the interpreter lock once
+ * per batch; argument meaning as in the two functions above. */
+int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames, int frames_on_device, int batch,
+                     int H, int W, double box_score, double nms_iou, int max_det, float* boxes_xywh,
+                     float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts,
+                     int32_t* n_candidates, int32_t* pts, int32_t* npts, uint8_t* status);
+
 /* decode only, from the 4 head tensors concatenated per frame ([batch, total_dim] fp32 host,
  * order loc_row, loc_col, exist_row, exist_col) */
 int adas_ufld_postprocess(int device, const float* heads_host, int batch, int num_grid_row,

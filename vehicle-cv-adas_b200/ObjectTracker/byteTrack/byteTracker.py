@@ -62,6 +62,14 @@ class BYTETracker(ObjectTrackBase):
     def _make(dets, scores, cids):
         return [STrack(STrack.tlbr_to_tlwh(b), s, c) for b, s, c in zip(dets, scores, cids)] if len(dets) > 0 else []
 
+    def _apply(self, matches, tracks, dets, activated, refind):
+        """Matched pairs of one stage: batched Kalman correction, then route to activated (was Tracked) / refind (was Lost)."""
+        pairs = [(tracks[it], dets[idet]) for it, idet in matches]
+        was_tracked = [t.state == TrackState.Tracked for t, _ in pairs]
+        STrack.multi_update(pairs, self.frame_id)
+        for (t, _), wt in zip(pairs, was_tracked):
+            (activated if wt else refind).append(t)
+
     def update(self, bboxes, scores, class_ids, frame=None):
         self.frame_id += 1
         activated, refind, lost, removed = [], [], [], []
@@ -78,26 +86,12 @@ class BYTETracker(ObjectTrackBase):
         pool = joint_stracks(tracked, self.lost_stracks)
         STrack.multi_predict(pool)
         matches, u_track, u_det = matching.associate(pool, detections, self.match_thresh, fuse=True)
-        for it, idet in matches:
-            t, d = pool[it], detections[idet]
-            if t.state == TrackState.Tracked:
-                t.update(d, self.frame_id)
-                activated.append(t)
-            else:
-                t.re_activate(d, self.frame_id, new_id=False)
-                refind.append(t)
+        self._apply(matches, pool, detections, activated, refind)
 
         # stage 2: still-tracked leftovers vs low-score detections (plain IoU, 0.5)
         r_tracked = [pool[i] for i in u_track if pool[i].state == TrackState.Tracked]
         matches, u_track2, _ = matching.associate(r_tracked, detections_second, 0.5, fuse=False)
-        for it, idet in matches:
-            t, d = r_tracked[it], detections_second[idet]
-            if t.state == TrackState.Tracked:
-                t.update(d, self.frame_id)
-                activated.append(t)
-            else:
-                t.re_activate(d, self.frame_id, new_id=False)
-                refind.append(t)
+        self._apply(matches, r_tracked, detections_second, activated, refind)
         for it in u_track2:
             t = r_tracked[it]
             if t.state != TrackState.Lost:
@@ -107,9 +101,7 @@ class BYTETracker(ObjectTrackBase):
         # stage 3: unconfirmed (one-frame-old) tracks vs leftover high detections (fused cost, 0.7)
         detections = [detections[i] for i in u_det]
         matches, u_unconf, u_det = matching.associate(unconfirmed, detections, 0.7, fuse=True)
-        for it, idet in matches:
-            unconfirmed[it].update(detections[idet], self.frame_id)
-            activated.append(unconfirmed[it])
+        self._apply(matches, unconfirmed, detections, activated, activated)
         for it in u_unconf:
             unconfirmed[it].mark_removed()
             removed.append(unconfirmed[it])

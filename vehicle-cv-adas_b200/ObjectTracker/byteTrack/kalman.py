@@ -51,3 +51,17 @@ def update(mean, cov, xyah):
     gain = scipy.linalg.cho_solve((chol, lower), np.dot(cov, H.T).T, check_finite=False).T
     innov = xyah - pm
     return mean + np.dot(innov, gain.T), cov - np.linalg.multi_dot((gain, pc, gain.T))
+
+
+def multi_update(means, covs, zs):
+    """Batched `update` for N (track, measurement) pairs: same algebra as kalman_filter.py:194-226 with the 4x4 systems
+    solved by one batched LAPACK call instead of N scipy Cholesky round trips (differences are at the 1e-16 level)."""
+    h = means[:, 3]
+    std = np.stack([W_POS * h, W_POS * h, np.full_like(h, 1e-1), W_POS * h], 1)
+    pm = means[:, :4]
+    pc = covs[:, :4, :4] + np.einsum("ni,ij->nij", np.square(std), np.eye(4))
+    gain_t = np.linalg.solve(pc, covs[:, :4, :])            # [N,4,8] = K^T  (pc symmetric)
+    innov = zs - pm
+    new_means = means + np.einsum("ni,nij->nj", innov, gain_t)
+    new_covs = covs - np.einsum("nia,nij,njb->nab", gain_t, pc, gain_t)
+    return new_means, new_covs

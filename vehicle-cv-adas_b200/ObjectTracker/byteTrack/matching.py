@@ -14,14 +14,16 @@ DEVICE = 0
 def _tlbrs(tracks):
     if len(tracks) > 0 and isinstance(tracks[0], np.ndarray):
         return np.ascontiguousarray(tracks, dtype=float).reshape(-1, 4)
-    return np.ascontiguousarray([t.tlbr for t in tracks], dtype=float).reshape(-1, 4)
+    from .strack import STrack
+    return np.ascontiguousarray(STrack.multi_tlbr(tracks))
 
 
 def iou_distance(atracks, btracks):
     a, b = _tlbrs(atracks), _tlbrs(btracks)
     if a.shape[0] == 0 or b.shape[0] == 0:
         return np.zeros((a.shape[0], b.shape[0]), dtype=float)
-    return _capi.iou_cost([a], [b], None, device=DEVICE)[0]
+    # the single-problem entry keeps its device scratch alive between calls (no cudaMalloc on the per-frame path)
+    return _capi.associate(a, b, None, 2.0, device=DEVICE, want_cost=True)[2]
 
 
 def fuse_score(cost_matrix, detections):

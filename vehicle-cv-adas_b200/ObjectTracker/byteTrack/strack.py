@@ -124,6 +124,47 @@ class STrack(BaseTrack):
         for t, m, c in zip(stracks, means, covs):
             t.mean, t.covariance = m, c
 
+    @staticmethod
+    def multi_tlbr(stracks):
+        """[N,4] tlbr of many tracks at once (same float operations as the `tlbr` property, vectorised)."""
+        if not stracks:
+            return np.zeros((0, 4), dtype=float)
+        out = np.empty((len(stracks), 4), dtype=float)
+        has = np.array([t.mean is not None for t in stracks])
+        if has.any():
+            m = np.asarray([t.mean[:4] for t, h in zip(stracks, has) if h])
+            w = m[:, 2] * m[:, 3]
+            x = m[:, 0] - w / 2
+            y = m[:, 1] - m[:, 3] / 2
+            out[has] = np.stack([x, y, w + x, m[:, 3] + y], 1)
+        if (~has).any():
+            r = np.asarray([t._tlwh for t, h in zip(stracks, has) if not h])
+            out[~has] = np.stack([r[:, 0], r[:, 1], r[:, 2] + r[:, 0], r[:, 3] + r[:, 1]], 1)
+        return out
+
+    @staticmethod
+    def multi_update(pairs, frame_id):
+        """Kalman-correct every matched (track, detection) pair of one association stage in one batched solve, then apply
+        the per-track bookkeeping of `update` (Tracked) / `re_activate` (Lost) -- strack.py:88-120 of the reference."""
+        if not pairs:
+            return
+        means = np.asarray([t.mean for t, _ in pairs])
+        covs = np.asarray([t.covariance for t, _ in pairs])
+        zs = np.asarray([STrack.tlwh_to_xyah(d.tlwh) for _, d in pairs])
+        nm, nc = kalman.multi_update(means, covs, zs)
+        for (t, d), m, c in zip(pairs, nm, nc):
+            t.mean, t.covariance = m, c
+            if t.state == TrackState.Tracked:
+                t.tracklet_len += 1
+                t.trajectories.append(d.tlbr)
+            else:
+                t.tracklet_len = 0
+            t.frame_id = frame_id
+            t.state = TrackState.Tracked
+            t.is_activated = True
+            t.score = d.score
+            t.update_class_id(d.class_id)
+
     def activate(self, frame_id):
         self.track_id = self.next_id()
         self.mean, self.covariance = kalman.initiate(self.tlwh_to_xyah(self._tlwh))

@@ -23,7 +23,7 @@ SYMBOLS = [
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
-    "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops",
+    "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_detect_pair",
 ]
 
 
@@ -171,6 +171,31 @@ class Engine:
         check(lib().adas_ufld_detect(self._h, fptr, 1 if on_device else 0, B, H, W, _p(pts, C.c_int32), _p(npts, C.c_int32),
                                      _p(status, C.c_uint8), _p(coords, C.c_double) if want_coords else None))
         return pts, npts, status, coords
+
+
+def detect_pair(yolo: "Engine", ufld: "Engine", frames, box_score: float, nms_iou: float, max_det: int = 300, on_device: bool = False, shape=None):
+    """One library call: YOLO detect then UFLD lane detect on the same frames -> (yolo tuple, ufld tuple)."""
+    if on_device:
+        ptr, (B, H, W) = frames, shape
+        fptr = C.cast(C.c_void_p(ptr), C.POINTER(C.c_uint8))
+    else:
+        frames = as_c(frames, np.uint8)
+        B, H, W = frames.shape[:3]
+        fptr = _p(frames, C.c_uint8)
+    boxes = np.empty((B, max_det, 4), np.float32)
+    scores = np.empty((B, max_det), np.float32)
+    cls = np.empty((B, max_det), np.int32)
+    idx = np.empty((B, max_det), np.int32)
+    counts = np.empty((B,), np.int32)
+    ncand = np.empty((B,), np.int32)
+    mp = max(ufld.output_shapes[0][2], ufld.output_shapes[1][2])
+    pts = np.empty((B, 4, mp, 2), np.int32)
+    npts = np.empty((B, 4), np.int32)
+    status = np.empty((B, 4), np.uint8)
+    check(lib().adas_detect_pair(yolo._h, ufld._h, fptr, 1 if on_device else 0, B, H, W, C.c_double(box_score), C.c_double(nms_iou), max_det,
+                                 _p(boxes, C.c_float), _p(scores, C.c_float), _p(cls, C.c_int32), _p(idx, C.c_int32), _p(counts, C.c_int32),
+                                 _p(ncand, C.c_int32), _p(pts, C.c_int32), _p(npts, C.c_int32), _p(status, C.c_uint8)))
+    return (boxes, scores, cls, idx, counts, ncand), (pts, npts, status, None)
 
 
 def yolo_postprocess(raw: np.ndarray, model_kind: int, n_classes: int, in_hw, src_hw, box_score: float, nms_iou: float,

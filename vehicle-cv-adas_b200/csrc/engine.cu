@@ -617,6 +617,14 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     return 0;
 }
 
+int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames, int frames_on_device, int batch, int H, int W, double box_score,
+                     double nms_iou, int max_det, float* boxes_xywh, float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts,
+                     int32_t* n_candidates, int32_t* pts, int32_t* npts, uint8_t* status) {
+    if (adas_yolo_detect(yolo, frames, frames_on_device, batch, H, W, box_score, nms_iou, max_det, boxes_xywh, scores, class_ids, cand_index, counts,
+                         n_candidates)) return 1;
+    return adas_ufld_detect(ufld, frames, frames_on_device, batch, H, W, pts, npts, status, nullptr);
+}
+
 int adas_ufld_postprocess(int device, const float* heads_host, int batch, int ngr, int ncr, int ngc, int ncc, int nl, int img_w, int img_h,
                           const double* row_anchor, const double* col_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords_f) {
     ADAS_CUDA(cudaSetDevice(device));

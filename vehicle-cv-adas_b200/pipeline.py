@@ -2,13 +2,15 @@
 
 demo.py does, per frame and strictly in sequence: `objectDetector.DetectFrame` (269) -> `objectTracker.update` (272-277)
 -> `laneDetector.DetectFrame` (280) -> analytics/drawing.  Here one step takes a batch of consecutive frames of one
-stream:  the object and lane networks run concurrently on their own engine handles / CUDA streams (two worker threads;
-the ctypes calls release the GIL), while the host thread runs the ByteTrack updates of the PREVIOUS batch -- the tracker
-is sequential in time per stream, so it pipelines one batch behind the detectors.  Per-frame results are
-identical to calling the three detectors frame by frame.
+stream:  a worker thread drives the object and lane networks back to back (the ctypes calls release the GIL; running
+the two persistent-kernel streams concurrently was measured SLOWER on B200 -- 10.0 vs 7.0 ms per 8-frame step -- because
+every conv kernel already fills all 148 SMs), while the host thread runs the ByteTrack updates of the PREVIOUS batch:
+the tracker is sequential in time per stream, so it pipelines one batch behind the detectors.  Per-frame
+results are identical to calling the three detectors frame by frame.
 """
 from __future__ import annotations
 
+import sys
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
 
@@ -36,7 +38,8 @@ class AdasPipeline:
         self.tracker = BYTETracker(names=class_names or [], device=device)
         self.tracker.reset()
         self.class_names = class_names
-        self._pool = ThreadPoolExecutor(max_workers=2)
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        sys.setswitchinterval(2e-4)       # the detector thread only needs the interpreter between two library calls
         self._pending: Optional[StepResult] = None
 
     def close(self):
@@ -45,10 +48,11 @@ class AdasPipeline:
         self.ufld.close()
 
     # -- stages -------------------------------------------------------------------------------------------
+    def _detect_both(self, frames, on_device: bool, shape):
+        return _capi.detect_pair(self.yolo, self.ufld, frames, self.box_score, self.box_nms_iou, self.max_det, on_device, shape)
+
     def _detect(self, frames, on_device: bool, shape):
-        fy = self._pool.submit(self.yolo.yolo_detect, frames, self.box_score, self.box_nms_iou, self.max_det, on_device, shape)
-        fu = self._pool.submit(self.ufld.ufld_detect, frames, on_device, shape)
-        return fy, fu
+        return self._pool.submit(self._detect_both, frames, on_device, shape)
 
     def _track(self, r: StepResult) -> None:
         out = []
@@ -64,19 +68,18 @@ class AdasPipeline:
     # -- public ---------------------------------------------------------------------------------------------
     def step(self, frames, on_device: bool = False, shape=None) -> StepResult:
         """Synchronous: detectors (concurrently), then the tracker for this batch."""
-        fy, fu = self._detect(frames, on_device, shape)
-        r = StepResult(fy.result(), fu.result())
+        r = StepResult(*self._detect_both(frames, on_device, shape))
         self._track(r)
         return r
 
     def step_pipelined(self, frames, on_device: bool = False, shape=None) -> Optional[StepResult]:
         """Submit this batch to the detectors and, while they run, track the previous batch.  Returns the previous batch's
         complete result (None on the first call); call flush() after the last batch."""
-        fy, fu = self._detect(frames, on_device, shape)
+        fut = self._detect(frames, on_device, shape)
         done = self._pending
         if done is not None:
             self._track(done)
-        self._pending = StepResult(fy.result(), fu.result())
+        self._pending = StepResult(*fut.result())
         return done
 
     def flush(self) -> Optional[StepResult]:

@@ -168,8 +168,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     copy_stream = torch.cuda.Stream()
-    stage = [torch.empty((B, FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=f"cuda:{local}") for _ in range(2)]
-    copy_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    NS = pipe.depth + 2            # staging slots: batches in flight + the one being uploaded
+    stage = [torch.empty((B, FRAME_H, FRAME_W, 3), dtype=torch.uint8, device=f"cuda:{local}") for _ in range(NS)]
+    copy_ev = [torch.cuda.Event() for _ in range(NS)]
 
     def upload(slot, j):            # pinned host -> device staging on a side stream (overlaps the previous batch's compute)
         with torch.cuda.stream(copy_stream):
@@ -184,12 +185,13 @@ def run_b200(args):
             if on_device:
                 ptr = dev_pool[j].data_ptr()
             else:
-                copy_ev[i % 2].synchronize()
+                copy_ev[i % NS].synchronize()
                 if i + 1 < n:
-                    upload((i + 1) % 2, (first + i + 1) % pool_batches)
-                ptr = stage[i % 2].data_ptr()
+                    upload((i + 1) % NS, (first + i + 1) % pool_batches)
+                ptr = stage[i % NS].data_ptr()
             gather(pipe.step_pipelined(ptr, True, (B, FRAME_H, FRAME_W)))
-        gather(pipe.flush())
+        for r in pipe.flush():
+            gather(r)
 
     def timed(on_device: bool):
         run_steps(Wm, 0, on_device)

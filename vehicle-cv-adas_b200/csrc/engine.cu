@@ -8,6 +8,7 @@
 #include "plan.h"
 #include "../../include/adas_b200.h"
 #include <stdarg.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -86,6 +87,23 @@ struct adas_engine {
 namespace adas {
 
 static size_t elem_size(uint32_t dtype) { return dtype == 1 ? 4 : 2; }
+
+// ADAS_B200_TRACE=1: per-phase device time (CUDA events on the handle's stream) + host wall time of each detect call
+struct PhaseTrace {
+    static bool enabled() { static int v = -1; if (v < 0) { const char* t = getenv("ADAS_B200_TRACE"); v = (t && t[0] == '1') ? 1 : 0; } return v == 1; }
+    cudaStream_t st; const char* name; cudaEvent_t ev[10]; const char* names[10]; int n = 0; double t0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    PhaseTrace(cudaStream_t s, const char* nm) : st(s), name(nm) { if (enabled()) { t0 = now(); mark("start"); } }
+    void mark(const char* nm) { if (!enabled() || n >= 10) return; cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], st); names[n] = nm; ++n; }
+    void report() {
+        if (!enabled()) return;
+        cudaEventSynchronize(ev[n - 1]);
+        fprintf(stderr, "[trace] %s host %.3f ms |", name, now() - t0);
+        for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s %.3f", names[i], ms); }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    }
+};
 
 static const void* tensor_ptr(const adas_engine* e, int idx) {
     if (idx < 0) return nullptr;
@@ -548,13 +566,22 @@ int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
         e->yp_max_det = max_det;
     }
     const uint8_t* dfr = nullptr;
+    PhaseTrace tr(e->stream, "yolo_detect");
     if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
+    tr.mark("h2d");
     const LetterboxGeom g = letterbox_geom(H, W, (int)e->hdr.in_h, (int)e->hdr.in_w);
     if (launch_yolo_pre(dfr, batch, g, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr, e->stream)) return 1;
+    tr.mark("pre");
     if (run_plan(e, batch)) return 1;
+    tr.mark("plan");
     if (head_decode(e, batch)) return 1;
+    tr.mark("decode");
     if (launch_yolo_post(e->d_raw, (int)e->hdr.model_kind, batch, A, nc, g, box_score, nms_iou, max_det, e->yp, e->stream)) return 1;
-    return copy_yolo_results(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, n_candidates, e->stream);
+    tr.mark("select+nms");
+    const int rc = copy_yolo_results(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, n_candidates, e->stream);
+    tr.mark("d2h");
+    tr.report();
+    return rc;
 }
 
 int adas_yolo_postprocess(int device, const float* raw_host, int model_kind, int batch, int n_anchors, int n_classes, int in_h,
@@ -596,12 +623,16 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
     ADAS_CUDA(cudaSetDevice(e->device));
     const uint8_t* dfr = nullptr;
+    PhaseTrace tr(e->stream, "ufld_detect");
     if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
+    tr.mark("h2d");
     const int in_h = (int)e->hdr.in_h, in_w = (int)e->hdr.in_w;
     const int resize_h = (int)((double)in_h / 0.6);   // int(self.input_height / cfg.crop_ratio), CULane crop_ratio 0.6
     if (launch_ufld_pre(dfr, batch, H, W, in_h, in_w, resize_h, e->d_lut, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr,
                         e->stream)) return 1;
+    tr.mark("pre");
     if (run_plan(e, batch)) return 1;
+    tr.mark("plan");
     const uint32_t* m = e->hdr.meta;
     UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
     const PlanOutput& o = e->outs[0];
@@ -614,6 +645,8 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     ADAS_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
     if (coords_f) ADAS_CUDA(cudaMemcpyAsync(coords_f, e->d_coords, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost, e->stream));
     ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    tr.mark("post+d2h");
+    tr.report();
     return 0;
 }
 

@@ -243,6 +243,9 @@ yolo_compact_nms_kernel(const float* __restrict__ raw, int kind, int A, int nc, 
             const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
             if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
         }
+        // Once every remaining score is 0 nothing can change any more (no swap: 0 < 0 is false; suppression only
+        // writes zeros), so the remaining iterations of the reference loop are no-ops: stop here.
+        if (!(bv > 0.0)) break;
         if (lane == 0 && SC[i] < bv) {
             // dets[i,:] <- dets[maxpos,:]; dets[maxpos,:] keeps its values (tBD is a view of row i)
             X1[i] = X1[bj]; Y1[i] = Y1[bj]; X2[i] = X2[bj]; Y2[i] = Y2[bj]; ID[i] = ID[bj];
@@ -252,6 +255,7 @@ yolo_compact_nms_kernel(const float* __restrict__ raw, int kind, int A, int nc, 
         __syncwarp();
         const double ix1 = X1[i], iy1 = Y1[i], ix2 = X2[i], iy2 = Y2[i], ia = AR[i];
         for (int j = p0 + lane; j < N; j += 32) {
+            if (SC[j] == 0.0) continue;                  // already suppressed: weight * 0 stays 0
             const double xx1 = fmax(ix1, X1[j]), yy1 = fmax(iy1, Y1[j]);
             const double xx2 = fmin(ix2, X2[j]), yy2 = fmin(iy2, Y2[j]);
             const double w = fmax(0.0, __dadd_rn(__dsub_rn(xx2, xx1), 1.0));

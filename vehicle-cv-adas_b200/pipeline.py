@@ -11,6 +11,7 @@ results are identical to calling the three detectors frame by frame.
 from __future__ import annotations
 
 import sys
+from collections import deque
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
 
@@ -31,7 +32,7 @@ class StepResult:
 
 class AdasPipeline:
     def __init__(self, yolo_plan: str, ufld_plan: str, device: int = 0, batch: int = 8, box_score: float = 0.4, box_nms_iou: float = 0.45,
-                 max_det: int = 300, class_names: Optional[List[str]] = None):
+                 max_det: int = 300, class_names: Optional[List[str]] = None, depth: int = 2):
         self.batch, self.box_score, self.box_nms_iou, self.max_det = batch, box_score, box_nms_iou, max_det
         self.yolo = _capi.Engine(yolo_plan, device, max_batch=batch)
         self.ufld = _capi.Engine(ufld_plan, device, max_batch=batch)
@@ -40,7 +41,8 @@ class AdasPipeline:
         self.class_names = class_names
         self._pool = ThreadPoolExecutor(max_workers=1)
         sys.setswitchinterval(2e-4)       # the detector thread only needs the interpreter between two library calls
-        self._pending: Optional[StepResult] = None
+        self.depth = max(1, depth)                     # batches in flight in the detector thread
+        self._queue = deque()
 
     def close(self):
         self._pool.shutdown(wait=True)
@@ -73,17 +75,20 @@ class AdasPipeline:
         return r
 
     def step_pipelined(self, frames, on_device: bool = False, shape=None) -> Optional[StepResult]:
-        """Submit this batch to the detectors and, while they run, track the previous batch.  Returns the previous batch's
-        complete result (None on the first call); call flush() after the last batch."""
-        fut = self._detect(frames, on_device, shape)
-        done = self._pending
-        if done is not None:
-            self._track(done)
-        self._pending = StepResult(*fut.result())
-        return done
+        """Queue this batch for the detector thread (up to `depth` batches in flight, so the GPU never waits for Python) and
+        return the oldest finished batch with its tracks (None while the pipeline fills); call flush() at the end.
+        Frame buffers must stay valid until their batch has been returned."""
+        self._queue.append(self._detect(frames, on_device, shape))
+        if len(self._queue) <= self.depth:
+            return None
+        r = StepResult(*self._queue.popleft().result())
+        self._track(r)
+        return r
 
-    def flush(self) -> Optional[StepResult]:
-        done, self._pending = self._pending, None
-        if done is not None:
-            self._track(done)
-        return done
+    def flush(self) -> List[StepResult]:
+        out = []
+        while self._queue:
+            r = StepResult(*self._queue.popleft().result())
+            self._track(r)
+            out.append(r)
+        return out

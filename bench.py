@@ -258,6 +258,8 @@ def run_b200(args):
                     "ms_per_step": round(ms_e2e / K, 4),
                     "note": "adas_b200.pipeline.AdasPipeline.step_pipelined: pinned host batch -> device staging (side stream), both detectors, tracker; results on the host every step"},
             "gpu_launches": int(launches),
+            "host_tracker_ms_per_step": round(1e3 * getattr(pipe, "track_seconds", 0.0) / max(1, getattr(pipe, "track_batches", 1)), 3),
+            "tracks_alive": len(pipe.tracker.tracked_stracks),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,

@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual=None, out_f32=False, pad=None, seed=0, im_c=None):
+    if pad is None and k == 1:
+        pad = 0
     rng = np.random.default_rng(seed)
     pb = plan.PlanBuilder(plan.MODEL_YOLOV5, 3, H, W)
     xin = pb.new_padded(H, W, im_c or cin)
@@ -68,6 +70,9 @@ CASES = [
     (1, 16, 32, 24, 24, 3, 1, 1, None, False),         # thin channels -> im2col path
     (1, 512, 8, 10, 50, 1, 1, 0, None, False),         # UFLD pool conv, N = 8
     (1, 64, 512, 8, 8, 3, 1, 1, None, False),          # M = 100 rows (one partial tile), N = 512
+    (1, 128, 256, 20, 28, 1, 2, 0, None, False),       # ResNet downsample: 1x1 stride 2 through the strided TMA map
+    (2, 256, 512, 40, 40, 3, 2, 1, None, False),       # stride-2 3x3, output 20x20 -> 20x6 patches, N = 512
+    (1, 64, 64, 160, 96, 3, 2, 2, "pre", False),       # stride-2 3x3 with residual, 48-wide output rows
 ]
 
 

@@ -55,6 +55,9 @@ struct GemmParams {
     int mask_H, mask_W;  // > 0: only rows in the interior of the padded (H+2)x(W+2) grid are stored
     int dbg;        // debug switches (ADAS_B200_DBG), 0 in production
     int mt_hint;    // v2 kernel: 1 forces single 128-row sub-tiles (more CTAs for small layers), 0 = auto
+    // stride-2 convs (3x3 pad 1, or 1x1) read the input through a 4-D TMA map with traversal stride 2: an M tile is a
+    // bw x bh patch of output pixels of one image; s2_* describe the output grid and the input's padded height
+    int s2, s2_bw, s2_bh, s2_tw, s2_th, s2_Ho, s2_Wo, s2_Hp_in;
     int transposed; // 1: out[n * out_ld + row] (swap-AB FC: rows = features, cols = batch), bias per row
     const float* bias;   // [N] ([M] when transposed) or nullptr
     const __half* res;   // residual, same row indexing as out, or nullptr
@@ -65,6 +68,8 @@ struct GemmParams {
 };
 
 struct GemmV2;
+int  gemm_tc_v2_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, uint64_t a_Wp, uint64_t a_Hp, uint64_t a_B, uint64_t a_ld,
+                           const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
 int  gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
                         const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
 int  gemm_tc_v2_run(void* opaque, cudaStream_t st);
@@ -75,6 +80,8 @@ int  gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPa
 int  gemm_simt_launch(const GemmParams& p, cudaStream_t st);
 int  gemm_tc_smem_bytes(int BN, int stages);
 int  gemm_tc_pick_stages(int BN, int num_kb);
+int  make_tmap_4d_s2(CUtensorMap* tm, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint64_t ld_elems,
+                     uint32_t box_w_src, uint32_t box_h_src);
 int  make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                   uint32_t box_inner, uint32_t box_rows);
 

@@ -121,11 +121,13 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 const int res_buf = p[8], res_coff = p[9], res_pre = p[10], out_buf = p[11], out_coff = p[12], masked = p[13];
                 const int transposed = p[14];
                 int BN = p[15];
+                const int s2 = p[16];
                 const PlanBuffer& ab = e->bufs[a_buf];
                 const PlanBuffer& ob = e->bufs[out_buf];
                 ADAS_CHECK(ab.dtype == 0, "op %zu: GEMM input buffer must be fp16", oi);
                 ADAS_CHECK(Kc % 8 == 0 && a_coff % 8 == 0 && ab.C % 8 == 0, "op %zu: K alignment", oi);
                 ADAS_CHECK(ntaps == 1 || (ntaps == 9 && Kc % 64 == 0 && ab.W > 0), "op %zu: tap mode needs Cin %% 64 == 0", oi);
+                ADAS_CHECK(!s2 || (Kc % 64 == 0 && ab.W > 0 && ob.W > 0 && !transposed), "op %zu: stride-2 mode needs Cin %% 64 == 0 on padded grids", oi);
                 GemmParams g;
                 memset(&g, 0, sizeof(g));
                 const int Ktot = ntaps * Kc;
@@ -138,7 +140,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 if (!transposed) {
                     g.M = a_rows;
                     g.N = N;
-                    if (BN <= 0) {
+                    if (BN <= 0 && !s2) {
                         if (e->conv_impl == 0 && !e->gemm_v1) {
                             gemm_tc_v2_choose(a_rows, N, Kc, ntaps, &BN, &g.mt_hint);
                         } else if (N <= 256) BN = (N + 15) / 16 * 16;
@@ -151,7 +153,28 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     opB = wptr; b_inner = (uint64_t)Ktot; b_rows_u = (uint64_t)N; b_stride = (uint64_t)Ktot * 2;
                     g.A = aptr; g.a_ld = (int)ab.C; g.Wt = wptr; g.w_ld = Ktot;
                     g.out_ld = (int)ob.C;
-                    ADAS_CHECK((int)ob.rows_per_img == (int)ab.rows_per_img, "op %zu: GEMM in/out row geometry differs", oi);
+                    ADAS_CHECK(s2 || (int)ob.rows_per_img == (int)ab.rows_per_img, "op %zu: GEMM in/out row geometry differs", oi);
+                    if (s2) {
+                        // output-pixel patch (bw x bh <= 128) that wastes the fewest rows of the 128-row MMA tile
+                        const int Ho = (int)ob.H, Wo = (int)ob.W;
+                        int best_bw = 8, best_bh = 16; double best_eff = -1.0;
+                        const int cands[] = {Wo, 128, 64, 32, 16, 8};
+                        for (int ci = 0; ci < 6; ++ci) {
+                            const int bw = cands[ci];
+                            if (bw < 1 || bw > 128) continue;
+                            const int bh = 128 / bw;
+                            if (bh < 1) continue;
+                            const int tw = (Wo + bw - 1) / bw, th = (Ho + bh - 1) / bh;
+                            const double eff = (double)Wo * Ho / ((double)tw * th * 128.0);
+                            if (eff > best_eff + 1e-9) { best_eff = eff; best_bw = bw; best_bh = bh; }
+                        }
+                        g.s2 = 1; g.s2_bw = best_bw; g.s2_bh = best_bh;
+                        g.s2_tw = (Wo + best_bw - 1) / best_bw; g.s2_th = (Ho + best_bh - 1) / best_bh;
+                        g.s2_Ho = Ho; g.s2_Wo = Wo; g.s2_Hp_in = (int)ab.H + 2;
+                        if (e->conv_impl == 1) g.M = batch * (int)ob.rows_per_img;        // SIMT kernel walks output rows
+                        else g.M = batch * g.s2_tw * g.s2_th * 128;                         // tcgen05 kernel walks patches
+                        if (p[15] <= 0) BN = N <= 256 ? (N + 15) / 16 * 16 : (N % 256 == 0 ? 256 : 128);
+                    }
                 } else {
                     // swap-AB: rows = output features (weights stream once through the A operand), cols = batch rows
                     g.M = N;
@@ -177,7 +200,10 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
                 if (e->conv_impl == 0 && !e->gemm_v1) {
                     void* opaque = nullptr;
-                    if (e->autotune && !transposed && p[15] <= 0) {
+                    if (s2) {
+                        if (gemm_tc_v2_prepare_s2(g, aptr, (uint64_t)Kc, (uint64_t)ab.W + 2, (uint64_t)ab.H + 2, (uint64_t)batch, (uint64_t)ab.C,
+                                                  opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
+                    } else if (e->autotune && !transposed && p[15] <= 0) {
                         // measure the modelled top candidates on the device once per (op, batch); every candidate accumulates in the
                         // same K order, so the choice never changes results
                         int cBN[6], cMT[6];
@@ -208,6 +234,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
                 } else if (e->conv_impl == 0) {
+                    ADAS_CHECK(!s2, "op %zu: the v1 kernel has no stride-2 mode (unset ADAS_B200_GEMM)", oi);
                     CUtensorMap tmA, tmB;
                     if (make_tmap_2d(&tmA, opA, a_inner, a_rows_u, a_stride, 64, 128)) return 1;
                     if (make_tmap_2d(&tmB, opB, b_inner, b_rows_u, b_stride, 64, (uint32_t)BN)) return 1;

@@ -58,6 +58,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -383,7 +389,8 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp_idx == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
-            const uint32_t tx_bytes = (uint32_t)(g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + taps_per_step * p.BN * BK * 2);
+            const uint32_t tx_bytes = p.s2 ? (uint32_t)(p.s2_bw * p.s2_bh * BK * 2 + p.BN * BK * 2)
+                                           : (uint32_t)(g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + taps_per_step * p.BN * BK * 2);
             uint32_t it = 0;
             for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
                 const int n0 = (t % g.n_tiles) * p.BN;
@@ -406,6 +413,17 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
                         for (int dx = 0; dx < 3; ++dx)
                             tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
+                    } else if (p.s2) {
+                        // stride-2 conv: tile = bw x bh output pixels of image b; input pixel of tap (dy,dx) is (2*yo+dy, 2*xo+dx)
+                        // in padded coordinates, fetched by one 4-D TMA box with traversal stride 2 in x and y
+                        const int mt_idx = t / g.n_tiles;
+                        const int per_img = p.s2_tw * p.s2_th;
+                        const int b = mt_idx / per_img;
+                        const int rem = mt_idx - b * per_img;
+                        const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
+                        const int dy = p.ntaps == 9 ? grp / 3 : 1, dx = p.ntaps == 9 ? grp % 3 : 1;
+                        tma_load_4d(a_dst, &tmA, kc * BK, 2 * tx * p.s2_bw + dx, 2 * ty * p.s2_bh + dy, b, fb);
+                        tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
                     } else {
                         int shift = 0;
                         if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
@@ -471,9 +489,20 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(smem_u32(&tfull_bar[as]), (tile_it >> 1) & 1u);
             tcgen05_fence_after();
             for (int mt = 0; mt < g.MT; ++mt) {
-                const int row = m0 + mt * BM + q * 32 + lane;
+                int row = m0 + mt * BM + q * 32 + lane;
                 bool row_ok = row < p.M;
-                if (p.mask_H > 0 && row_ok) {
+                if (p.s2) {
+                    const int r = q * 32 + lane;
+                    const int mt_idx = t / g.n_tiles;
+                    const int per_img = p.s2_tw * p.s2_th;
+                    const int b = mt_idx / per_img;
+                    const int rem = mt_idx - b * per_img;
+                    const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
+                    const int j = r / p.s2_bw, i = r - j * p.s2_bw;
+                    const int yo = ty * p.s2_bh + j, xo = tx * p.s2_bw + i;
+                    row_ok = (r < p.s2_bw * p.s2_bh) && (yo < p.s2_Ho) && (xo < p.s2_Wo);
+                    row = (b * (p.s2_Ho + 2) + yo + 1) * (p.s2_Wo + 2) + xo + 1;
+                } else if (p.mask_H > 0 && row_ok) {
                     const int Wp = p.mask_W + 2;
                     const int img = (p.mask_H + 2) * Wp;
                     const int pp = row % img;
@@ -588,12 +617,12 @@ static int g_num_sms = 0;
 int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
     g->p = p;
     g->MT = (p.BN <= 128) ? 2 : 1;
-    if (p.mt_hint == 1) g->MT = 1;
+    if (p.mt_hint == 1 || p.s2) g->MT = 1;
     const int b_bytes = ((p.BN * BK * 2) + 1023) & ~1023;
     g->b_bytes = b_bytes;
     const int budget = 218 * 1024;
     g->slab = 0;
-    if (p.ntaps == 9) {
+    if (p.ntaps == 9 && !p.s2) {
         const int slab_stage = g->MT * SLAB_BYTES + 3 * b_bytes;
         if (2 * slab_stage <= budget) g->slab = 1;
     }
@@ -710,6 +739,20 @@ int gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner
     return 0;
 }
 
+int gemm_tc_v2_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, uint64_t a_Wp, uint64_t a_Hp, uint64_t a_B, uint64_t a_ld,
+                          const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque) {
+    ADAS_CHECK(p.s2 && p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256 && p.N % 8 == 0, "gemm_tc_v2_s2: bad tile (BN %d)", p.BN);
+    GemmV2Launch* L = new GemmV2Launch();
+    if (gemm_tc_v2_config(p, &L->g)) { delete L; ADAS_CHECK(false, "gemm_tc_v2_s2: tile does not fit in shared memory"); }
+    if (make_tmap_4d_s2(&L->tmA, a_base, a_C, a_Wp, a_Hp, a_B, a_ld, 2u * (uint32_t)p.s2_bw, 2u * (uint32_t)p.s2_bh) ||
+        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)p.BN)) {
+        delete L;
+        return 1;
+    }
+    *opaque = L;
+    return 0;
+}
+
 int gemm_tc_v2_run(void* opaque, cudaStream_t st) {
     GemmV2Launch* L = static_cast<GemmV2Launch*>(opaque);
     return gemm_tc_v2_launch(L->tmA, L->tmB, L->g, st);
@@ -787,6 +830,22 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t row
     return 0;
 }
 
+int make_tmap_4d_s2(CUtensorMap* tm, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint64_t ld_elems,
+                    uint32_t box_w_src, uint32_t box_h_src) {
+    PFN_encodeTiled fn = get_encode_fn();
+    ADAS_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    ADAS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0, "TMA 4-D map alignment");
+    ADAS_CHECK(box_w_src <= 256 && box_h_src <= 256, "TMA 4-D box too large (%u x %u)", box_w_src, box_h_src);
+    cuuint64_t dims[4] = {C, Wp, Hp, B};
+    cuuint64_t strides[3] = {ld_elems * 2, Wp * ld_elems * 2, Hp * Wp * ld_elems * 2};
+    cuuint32_t box[4] = {64, box_w_src, box_h_src, 1};
+    cuuint32_t estr[4] = {1, 2, 2, 1};          // traversal stride 2 in x and y: the box delivers ceil(box/2) pixels per axis
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ADAS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4-D, stride 2) failed: %d", (int)r);
+    return 0;
+}
+
 // ---- SIMT validation kernel: same contract, CUDA cores, fp32 accumulate ---------------------------
 __global__ void gemm_simt_kernel(const GemmParams p) {
     const int row = blockIdx.x * 64 + (threadIdx.x >> 2);       // 64 rows per block
@@ -810,8 +869,16 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     for (int tap = 0; tap < p.ntaps; ++tap) {
         int shift = 0;
         if (p.ntaps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-        const long ar = (long)row + shift;
-        if (ar < 0 || ar >= p.M) continue;
+        long ar = (long)row + shift;
+        if (p.s2) {
+            // out row -> (b, yo, xo); input pixel (2*yo+dy, 2*xo+dx) in the input's padded grid
+            const int Wop = p.mask_W + 2, img = (p.mask_H + 2) * Wop;
+            const int b = row / img, pp = row - b * img;
+            const int yo = pp / Wop - 1, xo = pp % Wop - 1;
+            const int dy = p.ntaps == 9 ? tap / 3 : 1, dx = p.ntaps == 9 ? tap % 3 : 1;
+            ar = ((long)b * p.s2_Hp_in + 2 * yo + dy) * p.Wp + 2 * xo + dx;
+        } else if (ar < 0 || ar >= p.M) continue;
+        if (ar < 0) continue;
         const __half* a = p.A + (size_t)ar * p.a_ld;
         for (int c = 0; c < p.Kc; ++c) {
             const float av = __half2float(a[c]);

@@ -57,6 +57,8 @@ class AdasPipeline:
         return self._pool.submit(self._detect_both, frames, on_device, shape)
 
     def _track(self, r: StepResult) -> None:
+        import time
+        t0 = time.perf_counter()
         out = []
         for b in range(len(r.counts)):
             n = int(r.counts[b])
@@ -66,6 +68,8 @@ class AdasPipeline:
             ids = r.class_ids[b, :n] if self.class_names is None else [self.class_names[c] for c in r.class_ids[b, :n]]
             out.append(self.tracker.update(xyxy, r.scores[b, :n], ids, None))
         r.tracks = out
+        self.track_seconds = getattr(self, "track_seconds", 0.0) + (time.perf_counter() - t0)
+        self.track_batches = getattr(self, "track_batches", 0) + 1
 
     # -- public ---------------------------------------------------------------------------------------------
     def step(self, frames, on_device: bool = False, shape=None) -> StepResult:

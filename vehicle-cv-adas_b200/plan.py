@@ -21,6 +21,7 @@ slices of a shared buffer (producers write their slice), so Concat/Split cost no
 from __future__ import annotations
 
 import math
+import os
 import re
 import struct
 import zlib
@@ -162,6 +163,7 @@ class PlanBuilder:
         self.outputs: List[Tuple[int, int, int, int]] = []
         self.meta = [0] * 16
         self.flops_per_img = 0   # 2*MAC of the convs/FCs as mathematically defined (no padding waste)
+        self.strided_tma = os.environ.get("ADAS_B200_STRIDED_TMA", "1") != "0"
         # buffer 0: the network input image, padded NHWC with C=4 (R,G,B,0)
         self.image = self.new_padded(in_h, in_w, 4)
 
@@ -216,10 +218,15 @@ class PlanBuilder:
                 b = np.concatenate([b, np.zeros(n_store - cout, np.float32)])
         bias_t = self.tensor(b.astype(np.float32)) if b is not None else -1
         res_buf, res_coff = (res.buf, res.coff) if res is not None else (-1, 0)
+        s2 = 0
         if k == 1 and s == 1 and pad == 0 and cin % 8 == 0:
             a, ntaps, Kc = x, 1, cin
         elif k == 3 and s == 1 and pad == 1 and cin % 64 == 0:
             a, ntaps, Kc = x, 9, cin
+        elif s == 2 and cin % 64 == 0 and ((k == 3 and pad == 1) or (k == 1 and pad == 0)) and x.H % 2 == 0 and x.W % 2 == 0 \
+                and self.strided_tma:
+            # stride-2 conv read straight from the padded input through a traversal-stride-2 TMA map (no patch matrix)
+            a, ntaps, Kc, s2 = x, k * k, cin, 1
         else:
             # patch gather into a [rows_out_padded, Kpad] matrix, then a plain GEMM
             assert cin % 4 == 0
@@ -232,7 +239,7 @@ class PlanBuilder:
                 wk = np.concatenate([wk, np.zeros((wk.shape[0], Kpad - wk.shape[1]), np.float32)], 1)
         w_t = self.tensor(wk.astype(np.float16))
         self._op(OP_GEMM, [a.buf, a.coff, Kc, ntaps, w_t, bias_t, n_store, act, res_buf, res_coff, 1 if res_pre_act else 0,
-                           out.buf, out.coff, 1, 0, 0])
+                           out.buf, out.coff, 1, 0, 0, s2])
         return View(out.buf, out.coff, cout, Ho, Wo)
 
     def maxpool(self, x: View, k: int, s: int, p: int, out: Optional[View] = None) -> View:

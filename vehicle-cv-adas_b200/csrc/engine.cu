@@ -57,6 +57,8 @@ struct adas_engine {
     bool use_graph = true;
     bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
+    int mc_mode = 0;              // ADAS_B200_MC: 0 single-CTA tiles, 1 TMA-multicast pairs (measured: no gain), 2 cta_group::2 MMA pairs,
+                                  // 3 autotune per layer between single CTAs and cta_group::2 pairs
     cudaStream_t stream = nullptr;
     PlanHeader hdr;
     std::vector<PlanBuffer> bufs;
@@ -211,9 +213,11 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                         float best_ms = 1e30f;
                         cudaEvent_t ev0, ev1;
                         ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1));
-                        for (int ci = 0; ci < nc; ++ci) {
+                        for (int cj = 0; cj < nc * (e->mc_mode == 3 ? 2 : 1); ++cj) {
+                            const int ci = cj % nc;
                             GemmParams gc = g;
                             gc.BN = cBN[ci]; gc.mt_hint = cMT[ci];
+                            gc.mc_hint = e->mc_mode == 3 ? (cj >= nc ? 2 : 0) : e->mc_mode;
                             void* cand = nullptr;
                             if (gemm_tc_v2_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &cand)) continue;
                             int rc = gemm_tc_v2_run(cand, e->stream);
@@ -230,7 +234,10 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                         }
                         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
                         ADAS_CHECK(opaque != nullptr, "op %zu: no GEMM tile configuration could be launched", oi);
-                    } else if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
+                    } else {
+                        g.mc_hint = (e->mc_mode == 1 || e->mc_mode == 2) ? e->mc_mode : 0;
+                        if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
+                    }
                     std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
                 } else if (e->conv_impl == 0) {
@@ -424,6 +431,8 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
+    const char* mcv = getenv("ADAS_B200_MC");
+    if (mcv) e->mc_mode = atoi(mcv);
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
     if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
     e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);

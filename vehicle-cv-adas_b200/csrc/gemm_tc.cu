@@ -64,6 +64,53 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint16_t mask) {
+    // multicast: the box lands at the same shared-memory offset (and signals the same barrier offset) in every CTA of `mask`
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants: one MMA spans both SMs of the pair (M = 256), each CTA stages its own 128 rows of
+// A and HALF of the weight tile; only the leader CTA (cluster rank 0) issues MMAs and commits.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -341,10 +388,18 @@ struct GemmV2 {
     int stage_bytes;
     int n_tiles, m_tiles, total_tiles;
     int use_base_offset;
+    int pair;        // 1: cta_group::2 -- the two CTAs of a cluster run ONE M=256 MMA per step, each staging half of the weight tile
+    int mc;          // 1: CTA pairs (cluster 2x1x1) on adjacent M tiles share every weight tile through TMA multicast
+    int work_items;  // scheduler items: tiles, or tile pairs when mc
 };
 
+// kCluster = false: plain launch, no cluster / cta_group::2 instructions in the binary (a kernel that contains them must be
+// launched with a cluster attribute).  kCluster = true: CTA pairs (TMA multicast or cta_group::2 MMA).
+template <bool kCluster>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmV2 g) {
+    const int g_pair = kCluster ? g.pair : 0;
+    const int g_mc = kCluster ? g.mc : 0;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
@@ -362,27 +417,40 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ksteps = (g.slab ? 3 : p.ntaps) * p.kpt;
     const int BMT = BM * g.MT;
     const int mt_cols = g.MT == 2 ? 128 : 0;      // TMEM column offset of sub-tile 1
+    // work distribution: item w -> (n tile, m tile).  With multicast pairs both CTAs of a cluster walk the same items and
+    // take the even / odd M tile of the pair, so they need the same weight tiles at the same time.
+    const int cl2 = (g_mc | g_pair);
+    const int crank = cl2 ? (int)cluster_ctarank() : 0;
+    const int w_first = cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+#define TILE_OF(w, nt_, mt_) const int nt_ = (w) % g.n_tiles; const int mt_ = cl2 ? 2 * ((w) / g.n_tiles) + crank : (w) / g.n_tiles;
 
     if (warp_idx == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), g_mc ? 2 : 1);     // multicast: both CTAs' MMA warps release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), V2_THREADS - 64);
+            mbar_init(smem_u32(&tempty_bar[s]), (V2_THREADS - 64) * (g_pair ? 2 : 1));   // pair: both CTAs' epilogues drain the leader's MMA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp_idx == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (g_pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (cl2) cluster_sync_all();          // peer barriers are initialised before any multicast / remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_holder;
 
@@ -392,15 +460,26 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t tx_bytes = p.s2 ? (uint32_t)(p.s2_bw * p.s2_bh * BK * 2 + p.BN * BK * 2)
                                            : (uint32_t)(g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + taps_per_step * p.BN * BK * 2);
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-                const int n0 = (t % g.n_tiles) * p.BN;
-                const int m0 = (t / g.n_tiles) * BMT;
+            const int half_rows = p.BN >> 1;
+            // pair mode: this CTA stages its own A rows + half of each weight tile; all bytes of both CTAs are accounted on the
+            // LEADER's full barrier (the leader expects 2x), the follower only issues its loads
+            const uint32_t pair_bytes = (uint32_t)(g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + taps_per_step * half_rows * BK * 2);
+            for (int w = w_first; w < g.work_items; w += w_step) {
+                if (p.dbg & 32) break;                     // DEBUG: no loads at all (MMA-rate experiment)
+                TILE_OF(w, n_t, m_t)
+                const int n0 = n_t * p.BN;
+                const int m0 = m_t * BMT;
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    const uint32_t fb = smem_u32(&full_bar[s]);
-                    mbar_expect_tx(fb, tx_bytes);
+                    uint32_t fb = smem_u32(&full_bar[s]);
+                    if (g_pair) {
+                        if (crank == 0) mbar_expect_tx(fb, 2u * pair_bytes);
+                        fb = mapa_rank(fb, 0);               // cluster address of the leader's barrier
+                    } else {
+                        mbar_expect_tx(fb, tx_bytes);
+                    }
                     // K order is (dy, k-block, dx) in BOTH modes so every output element accumulates in the same order
                     // whatever tile shape the autotuner picks (bit-identical results across batch sizes).
                     int grp, kc;
@@ -410,13 +489,20 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t b_dst = a_dst + g.MT * g.a_sub_bytes;
                     if (g.slab) {
                         const int r0 = m0 + (grp - 1) * p.Wp - 1;
-                        for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
-                        for (int dx = 0; dx < 3; ++dx)
-                            tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
+                        for (int mt = 0; mt < g.MT; ++mt) {
+                            if (g_pair) tma_load_2d_pair(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
+                            else tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
+                        }
+                        for (int dx = 0; dx < 3; ++dx) {
+                            if (g_pair) tma_load_2d_pair(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0 + crank * half_rows, fb);
+                            else if (g_mc) tma_load_2d_mc(b_dst + dx * g.b_bytes + crank * half_rows * 128, &tmB, (grp * 3 + dx) * p.Kc + kc * BK,
+                                                     n0 + crank * half_rows, fb, (uint16_t)3);
+                            else tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
+                        }
                     } else if (p.s2) {
                         // stride-2 conv: tile = bw x bh output pixels of image b; input pixel of tap (dy,dx) is (2*yo+dy, 2*xo+dx)
                         // in padded coordinates, fetched by one 4-D TMA box with traversal stride 2 in x and y
-                        const int mt_idx = t / g.n_tiles;
+                        const int mt_idx = m_t;
                         const int per_img = p.s2_tw * p.s2_th;
                         const int b = mt_idx / per_img;
                         const int rem = mt_idx - b * per_img;
@@ -427,18 +513,30 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     } else {
                         int shift = 0;
                         if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
-                        for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
-                        tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
+                        for (int mt = 0; mt < g.MT; ++mt) {
+                            if (g_pair) tma_load_2d_pair(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
+                            else tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
+                        }
+                        if (g_pair) tma_load_2d_pair(b_dst, &tmB, grp * p.Kc + kc * BK, n0 + crank * half_rows, fb);
+                        else if (g_mc) tma_load_2d_mc(b_dst + crank * half_rows * 128, &tmB, grp * p.Kc + kc * BK, n0 + crank * half_rows, fb, (uint16_t)3);
+                        else tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
                     }
                 }
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        if (!(g_pair && crank != 0)) {
+            // ================= MMA issuer (pair mode: leader CTA only, M = 256 across both SMs) =================
+            // The WHOLE warp walks the loop and waits on the barriers; one elected lane issues tcgen05.mma / commit.  Keeping the
+            // control flow warp-uniform lets the compiler hold descriptors and addresses in uniform registers -- with a
+            // single-lane loop every UTCHMMA operand went through R2UR and the issue rate, not the tensor pipe, set the pace.
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((g_pair ? 2 * BM : BM) >> 4) << 24);
+            const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const uint32_t a_step = (uint32_t)g.a_sub_bytes >> 4, b_step = (uint32_t)g.b_bytes >> 4;
+            const int n_dx = taps_per_step, n_mt = g.MT;
+            const bool skip_mma = (p.dbg & 2) != 0, no_wait = (p.dbg & 32) != 0;
             uint32_t it = 0, tile_it = 0;
-            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tile_it) {
+            for (int w = w_first; w < g.work_items; w += w_step, ++tile_it) {
                 const int as = tile_it & 1;
                 mbar_wait(smem_u32(&tempty_bar[as]), ((tile_it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
                 tcgen05_fence_after();
@@ -446,26 +544,38 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    if (!no_wait) mbar_wait(smem_u32(&full_bar[s]), ph);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_base + s * g.stage_bytes;
-                    const uint32_t b_addr = a_addr + g.MT * g.a_sub_bytes;
-                    for (int dx = 0; dx < taps_per_step; ++dx) {
-                        if (p.dbg & 2) break;
-                        for (int mt = 0; mt < g.MT; ++mt) {
-                            const uint32_t a_sub = a_addr + mt * g.a_sub_bytes + (g.slab ? dx * 128 : 0);
-                            const uint32_t b_sub = b_addr + dx * g.b_bytes;
+                    const uint32_t a_lo = ((smem_base + s * g.stage_bytes) & 0x3FFFFu) >> 4;      // 16-byte units
+                    const uint32_t b_lo = a_lo + (uint32_t)n_mt * a_step;
+                    if (elect_one()) {
+                        if (!skip_mma) {
+                            for (int dx = 0; dx < n_dx; ++dx) {
+                                for (int mt = 0; mt < n_mt; ++mt) {
+                                    const uint32_t a_sub = a_lo + (uint32_t)mt * a_step + (g.slab ? (uint32_t)dx * 8u : 0u);   // +dx rows of 128 B
+                                    const uint32_t b_sub = b_lo + (uint32_t)dx * b_step;
+                                    const uint32_t d = d_base + (uint32_t)(mt * mt_cols);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                const uint64_t ad = g.use_base_offset ? make_smem_desc_off(a_sub + k * 32) : make_smem_desc(a_sub + k * 32);
-                                const uint64_t bd = make_smem_desc(b_sub + k * 32);
-                                umma_f16(d_base + (uint32_t)(mt * mt_cols), ad, bd, idesc, (uint32_t)((ks | dx | k) != 0));
+                                    for (int k = 0; k < BK / 16; ++k) {
+                                        const uint64_t ad = desc_hi | (uint64_t)(a_sub + 2u * k);
+                                        const uint64_t bd = desc_hi | (uint64_t)(b_sub + 2u * k);
+                                        if (g_pair) umma_f16_pair(d, ad, bd, idesc, (uint32_t)((ks | dx | k) != 0));
+                                        else umma_f16(d, ad, bd, idesc, (uint32_t)((ks | dx | k) != 0));
+                                    }
+                                }
                             }
                         }
+                        if (g_pair) umma_commit_pair(smem_u32(&empty_bar[s]), (uint16_t)3);
+                        else if (g_mc) umma_commit_mc(smem_u32(&empty_bar[s]), (uint16_t)3);   // frees the stage in both CTAs of the pair
+                        else umma_commit(smem_u32(&empty_bar[s]));
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&tfull_bar[as]));
+                if (elect_one()) {
+                    if (g_pair) umma_commit_pair(smem_u32(&tfull_bar[as]), (uint16_t)3);      // both epilogues may read their TMEM halves
+                    else umma_commit(smem_u32(&tfull_bar[as]));
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -477,10 +587,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int half = (warp_idx - 2) >> 2;
         const int et = threadIdx.x - 64;
         uint32_t tile_it = 0;
-        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++tile_it) {
+        for (int w = w_first; w < g.work_items; w += w_step, ++tile_it) {
             const int as = tile_it & 1;
-            const int n0 = (t % g.n_tiles) * p.BN;
-            const int m0 = (t / g.n_tiles) * BMT;
+            TILE_OF(w, n_t, m_t)
+            const int n0 = n_t * p.BN;
+            const int m0 = m_t * BMT;
             if (!p.transposed) {
                 for (int j = et; j < p.BN; j += V2_THREADS - 64)
                     s_bias[as][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -493,7 +604,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 bool row_ok = row < p.M;
                 if (p.s2) {
                     const int r = q * 32 + lane;
-                    const int mt_idx = t / g.n_tiles;
+                    const int mt_idx = m_t;
                     const int per_img = p.s2_tw * p.s2_th;
                     const int b = mt_idx / per_img;
                     const int rem = mt_idx - b * per_img;
@@ -600,16 +711,20 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[as]));      // this thread is done reading accumulator stage `as`
+            if (g_pair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA waits for both epilogues
+            else mbar_arrive(smem_u32(&tempty_bar[as]));      // this thread is done reading accumulator stage `as`
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    if (cl2) cluster_sync_all();           // the peer may still multicast into this CTA's shared memory / arrive on its barriers
     if (warp_idx == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (g_pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+#undef TILE_OF
 }
 
 static int g_num_sms = 0;
@@ -618,7 +733,8 @@ int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
     g->p = p;
     g->MT = (p.BN <= 128) ? 2 : 1;
     if (p.mt_hint == 1 || p.s2) g->MT = 1;
-    const int b_bytes = ((p.BN * BK * 2) + 1023) & ~1023;
+    const int want_pair = (p.mc_hint == 2 && !p.s2 && p.BN % 32 == 0) ? 1 : 0;
+    const int b_bytes = ((((want_pair ? p.BN / 2 : p.BN)) * BK * 2) + 1023) & ~1023;
     g->b_bytes = b_bytes;
     const int budget = 218 * 1024;
     g->slab = 0;
@@ -636,6 +752,9 @@ int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
     g->n_tiles = (p.N + p.BN - 1) / p.BN;
     g->m_tiles = (p.M + BMT - 1) / BMT;
     g->total_tiles = g->n_tiles * g->m_tiles;
+    g->mc = (p.mc_hint == 1 && !p.s2 && g->m_tiles >= 2) ? 1 : 0;
+    g->pair = want_pair;
+    g->work_items = (g->mc | g->pair) ? g->n_tiles * ((g->m_tiles + 1) / 2) : g->total_tiles;
     const char* bo = getenv("ADAS_B200_BASEOFF");
     g->use_base_offset = (bo && bo[0] == '1');   // measured on B200: the swizzle phase follows the absolute smem address, the field stays 0
     static int dbg = -1;
@@ -656,15 +775,33 @@ int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
 int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmV2& g, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
         int dev = 0;
         ADAS_CUDA(cudaGetDevice(&dev));
         ADAS_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr = true;
     }
     const int smem = g.p.stages * g.stage_bytes + 1024;
+    if (g.mc | g.pair) {
+        const int pairs_max = g_num_sms / 2;
+        const int pairs = g.work_items < pairs_max ? g.work_items : pairs_max;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs, 1, 1);
+        cfg.blockDim = dim3(V2_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr1;
+        attr1.id = cudaLaunchAttributeClusterDimension;
+        attr1.val.clusterDim.x = 2; attr1.val.clusterDim.y = 1; attr1.val.clusterDim.z = 1;
+        cfg.attrs = &attr1;
+        cfg.numAttrs = 1;
+        ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<true>, tmA, tmB, g));
+        count_launch();
+        return 0;
+    }
     int grid = g.total_tiles < g_num_sms ? g.total_tiles : g_num_sms;
-    gemm_tc_v2_kernel<<<grid, V2_THREADS, smem, st>>>(tmA, tmB, g);
+    gemm_tc_v2_kernel<false><<<grid, V2_THREADS, smem, st>>>(tmA, tmB, g);
     count_launch();
     ADAS_CUDA(cudaGetLastError());
     return 0;
@@ -675,6 +812,7 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 // clock from L2 while its tensor pipe retires 4096 MACs per clock, so a tile is modelled by max(operand bytes / 32,
 // MMA clocks, epilogue clocks) and layers are charged whole waves of 148 persistent CTAs.
 int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out) {
+    // (the multicast on/off variants of each returned candidate are tried by the autotuner in engine.cu)
     const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
     struct C { double t; int BN, mt; } list[24];
     int n = 0;
@@ -731,7 +869,7 @@ int gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner
     if (gemm_tc_v2_config(p, &L->g)) { delete L; ADAS_CHECK(false, "gemm_tc_v2: tile does not fit in shared memory (BN %d)", p.BN); }
     const uint32_t a_box_rows = L->g.slab ? SLAB_ROWS : BM;
     if (make_tmap_2d(&L->tmA, a_base, a_inner, a_rows, a_stride_bytes, 64, a_box_rows) ||
-        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)p.BN)) {
+        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)((L->g.mc | L->g.pair) ? p.BN / 2 : p.BN))) {
         delete L;
         return 1;
     }

@@ -158,6 +158,34 @@ int adas_associate(int device, int T, int D, const double* a_tlbr, const double*
                    const double* det_scores, int fuse, double thresh, int32_t* x, int32_t* y,
                    double* cost_out);
 
+/* ---- native ByteTrack --------------------------------------------------------------------------------------------------
+ * adas_tracker_* replace BYTETracker.__init__/update/reset and the STrack / KalmanFilter records
+ * (ObjectTracker/byteTrack/byteTracker.py:31-60,62-185,187-200; dtypes/strack.py; dtypes/kalman_filter.py:55-226;
+ * utils.py:9-69).  The three association stages of update() run on the device (iou_cost + lap kernels); Kalman
+ * algebra (float64) and list bookkeeping run in host C++.  class ids are ints (the Python wrapper maps labels).
+ * The track-id counter is process-global like BaseTrack._count (base_track.py:12); adas_tracker_reset zeroes it. */
+typedef struct adas_tracker adas_tracker;
+typedef struct adas_track {
+    int32_t track_id, state /* 0 new 1 tracked 2 lost 3 removed */, is_activated, class_id;
+    int32_t start_frame, frame_id, tracklet_len, pad;
+    double score;
+    double tlwh[4];      /* current box (Kalman state), top-left x, y, w, h */
+    double mean[8];      /* Kalman mean (cx, cy, a, h, velocities) */
+    double det_tlbr[4];  /* detection matched in the last update() of a tracked track (STrack.trajectories entry) */
+    int32_t traj_frame;  /* frame_id at which det_tlbr was recorded (0 = never) */
+    int32_t pad2;
+} adas_track;
+int adas_tracker_create(int device, double track_thresh, int track_buffer, double match_thresh, int frame_rate,
+                        adas_tracker** out);
+int adas_tracker_destroy(adas_tracker* t);
+int adas_tracker_reset(adas_tracker* t);
+/* one frame: boxes_xyxy [n,4] float64 (demo.py feeds int-truncated RectInfo.tolist("xyxy")), scores [n], class_ids [n];
+ * writes up to max_out tracked tracks (tracked_stracks order) and their count */
+int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores,
+                        const int32_t* class_ids, int max_out, adas_track* out, int* n_out);
+int adas_tracker_get(adas_tracker* t, int which /* 0 tracked, 1 lost, 2 removed */, int max_out, adas_track* out, int* n_out);
+int adas_tracker_count(void);    /* BaseTrack._count */
+
 /* ---- test hooks (no reference counterpart): raw access to the plan's activation buffers so single kernels can be
  * parity-tested.  Buffers are [batch * rows_per_img, C] matrices (fp16 or fp32) as described in csrc/plan.h. */
 int adas_engine_num_buffers(const adas_engine* e, int* n);

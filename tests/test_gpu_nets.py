@@ -171,11 +171,13 @@ def test_engine_protocol_and_detector_api(tmp_path):
         UltrafastLaneDetectorV2(upath, LaneModelType.UFLDV2_CURVELANES, None)
 
 
-def test_bytetracker_matches_reference_golden(golden_dir):
-    from adas_b200.ObjectTracker import BYTETracker
+@pytest.mark.parametrize("impl", ["native", "python"])
+def test_bytetracker_matches_reference_golden(golden_dir, impl):
+    from adas_b200.ObjectTracker import BYTETracker, BYTETrackerPy
     g = np.load(os.path.join(golden_dir, "track.npz"))
+    cls_ = BYTETracker if impl == "native" else BYTETrackerPy
     for seed, nobj in ((0, 8), (1, 14), (2, 4), (3, 25)):
-        trk = BYTETracker(names=[])
+        trk = cls_(names=[])
         trk.reset()
         rows = []
         for f, (boxes, scores, labels) in enumerate(synth.track_sequence(seed, frames=45, objects=nobj)):

@@ -10,7 +10,7 @@ import numpy as np
 
 from ..core import ObjectTrackBase
 from . import matching
-from .strack import BaseTrack, STrack, TrackState
+from .strack import BaseTrack, LimitedList, STrack, TrackState
 
 
 def joint_stracks(a, b):
@@ -43,7 +43,9 @@ def remove_duplicate_stracks(a, b):
     return [t for i, t in enumerate(a) if i not in dup_a], [t for i, t in enumerate(b) if i not in dup_b]
 
 
-class BYTETracker(ObjectTrackBase):
+class BYTETrackerPy(ObjectTrackBase):
+    """Python state machine (kept for A/B tests); `BYTETracker` below is the native one the product uses."""
+
     def __init__(self, track_thresh=0.5, track_buffer=30, match_thresh=0.8, frame_rate=30, min_box_area=10, device=0, **kwargs):
         super().__init__(**kwargs)
         self.tracked_stracks, self.lost_stracks, self.removed_stracks = [], [], []
@@ -134,6 +136,133 @@ class BYTETracker(ObjectTrackBase):
         self.frame_id = 0
         self.tracked_stracks, self.lost_stracks, self.removed_stracks = [], [], []
         BaseTrack.reset_counter()
+
+    def DrawTrackedOnFrame(self, frame, show_box=True, show_traject=True):
+        for t in [t for t in self.tracked_stracks if t.is_activated]:
+            tlwh = t.tlwh
+            if tlwh[2] * tlwh[3] > self.min_box_area:
+                if show_box:
+                    self.plot_bbox(frame, tlwh, t.class_id, t.track_id)
+                if show_traject:
+                    self.plot_trajectories(frame, t.trajectories, t.class_id, t.track_id)
+                    self.plot_directions(frame, t.xyah, t.filter_trajectories(frame, (10, 10)), t.class_id)
+
+
+class TrackView:
+    """Read-only view of one native track with the attribute surface of the reference's STrack (strack.py:33-215)."""
+    __slots__ = ("track_id", "is_activated", "state", "score", "class_id", "start_frame", "frame_id", "tracklet_len", "mean", "_tlwh",
+                 "trajectories", "crops", "time_since_update", "location")
+
+    def __init__(self):
+        self.trajectories = LimitedList(30)
+        self.crops = []
+        self.time_since_update = 0
+        self.location = (np.inf, np.inf)
+
+    @property
+    def tlwh(self):
+        return self._tlwh.copy()
+
+    @property
+    def tlbr(self):
+        r = self._tlwh.copy()
+        r[2:] += r[:2]
+        return r
+
+    @property
+    def xyah(self):
+        return STrack.tlwh_to_xyah(self._tlwh)
+
+    @property
+    def end_frame(self):
+        return self.frame_id
+
+    def filter_trajectories(self, frame, pad=(0, 0)):
+        ph, pw = pad
+        return [b for b in list(self.trajectories)
+                if b[0] >= pw and b[1] >= ph and b[2] <= frame.shape[1] - pw and b[3] <= frame.shape[0] - ph]
+
+    def get_track_message(self, count):
+        return {"track_id": self.track_id, "count": count, "is_activated": self.is_activated, "state": self.state, "score": self.score,
+                "start_frame_number": self.start_frame, "curr_frame_number": self.frame_id, "time_since_update": self.time_since_update,
+                "location": str(self.location), "crops": self.crops, "class_id": self.class_id}
+
+    def __repr__(self):
+        return f"OT_{self.track_id}_({self.start_frame}-{self.end_frame})"
+
+
+class BYTETracker(ObjectTrackBase):
+    """The reference's BYTETracker API (byteTracker.py:12-215) over the native tracker (csrc/tracker.cu): `update` is one
+    library call per frame -- Kalman + bookkeeping in host C++, the three association stages on the device."""
+
+    def __init__(self, track_thresh=0.5, track_buffer=30, match_thresh=0.8, frame_rate=30, min_box_area=10, device=0, **kwargs):
+        super().__init__(**kwargs)
+        from ... import _capi
+        self._capi = _capi
+        self._nt = _capi.NativeTracker(device, track_thresh, track_buffer, match_thresh, frame_rate)
+        self.track_thresh, self.match_thresh, self.min_box_area = track_thresh, match_thresh, min_box_area
+        self.det_thresh = track_thresh + 0.1
+        self.buffer_size = int(frame_rate / 30.0 * track_buffer)
+        self.max_time_lost = self.buffer_size
+        self.frame_id = 0
+        self._labels, self._label_list = {}, []
+        self._views = {}
+        self.tracked_stracks = []
+        self.removed_stracks = []
+
+    def _cid(self, label):
+        k = label.item() if hasattr(label, "item") else label
+        i = self._labels.get(k)
+        if i is None:
+            i = self._labels[k] = len(self._label_list)
+            self._label_list.append(k)
+        return i
+
+    def _view(self, rec, frame=None):
+        tid = int(rec["track_id"])
+        v = self._views.get(tid)
+        if v is None:
+            v = self._views[tid] = TrackView()
+            if frame is not None:                      # STrack.update_crops at birth (strack.py:131-143, byteTracker.py:167)
+                tx1, ty1, tw, th = rec["tlwh"].astype(int)
+                x1, y1 = max(0, tx1), max(0, ty1)
+                x2, y2 = min(frame.shape[1], tx1 + tw), min(frame.shape[0], ty1 + th)
+                v.crops.append(frame[y1:y2, x1:x2, :].copy())
+        v.track_id, v.is_activated, v.state = tid, bool(rec["is_activated"]), int(rec["state"])
+        v.score, v.class_id = float(rec["score"]), self._label_list[int(rec["class_id"])]
+        v.start_frame, v.frame_id, v.tracklet_len = int(rec["start_frame"]), int(rec["frame_id"]), int(rec["tracklet_len"])
+        v.mean, v._tlwh = rec["mean"].copy(), rec["tlwh"].copy()
+        if int(rec["traj_frame"]) == self.frame_id:
+            v.trajectories.append(rec["det_tlbr"].copy())
+        return v
+
+    def update(self, bboxes, scores, class_ids, frame=None):
+        self.frame_id += 1
+        ids = np.fromiter((self._cid(c) for c in class_ids), dtype=np.int32, count=len(class_ids)) if len(class_ids) else np.zeros(0, np.int32)
+        recs = self._nt.update(np.asarray(bboxes, dtype=np.float64).reshape(-1, 4), np.asarray(scores, dtype=np.float64), ids)
+        self.tracked_stracks = [self._view(r, frame) for r in recs]
+        if len(self._views) > 4 * max(64, len(recs)):                 # forget views of long-gone tracks
+            alive = {int(r["track_id"]) for r in recs} | {int(r["track_id"]) for r in self._nt.get(1)}
+            self._views = {k: v for k, v in self._views.items() if k in alive}
+        cnt = self._capi.NativeTracker.count()
+        return [t.get_track_message(cnt) for t in self.tracked_stracks]
+
+    @property
+    def lost_stracks(self):
+        out = []
+        for r in self._nt.get(1):
+            v = self._views.get(int(r["track_id"])) or TrackView()
+            v.track_id, v.is_activated, v.state = int(r["track_id"]), bool(r["is_activated"]), int(r["state"])
+            v.score, v.class_id = float(r["score"]), self._label_list[int(r["class_id"])]
+            v.start_frame, v.frame_id, v.tracklet_len = int(r["start_frame"]), int(r["frame_id"]), int(r["tracklet_len"])
+            v.mean, v._tlwh = r["mean"].copy(), r["tlwh"].copy()
+            out.append(v)
+        return out
+
+    def reset(self):
+        self.frame_id = 0
+        self.tracked_stracks, self.removed_stracks, self._views = [], [], {}
+        self._nt.reset()
 
     def DrawTrackedOnFrame(self, frame, show_box=True, show_traject=True):
         for t in [t for t in self.tracked_stracks if t.is_activated]:

@@ -24,6 +24,7 @@ SYMBOLS = [
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_detect_pair",
+    "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_get", "adas_tracker_count",
 ]
 
 
@@ -55,6 +56,60 @@ def _p(a: np.ndarray, typ):
 
 def as_c(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+class TrackRec(C.Structure):
+    _fields_ = [("track_id", C.c_int32), ("state", C.c_int32), ("is_activated", C.c_int32), ("class_id", C.c_int32),
+                ("start_frame", C.c_int32), ("frame_id", C.c_int32), ("tracklet_len", C.c_int32), ("pad", C.c_int32),
+                ("score", C.c_double), ("tlwh", C.c_double * 4), ("mean", C.c_double * 8), ("det_tlbr", C.c_double * 4), ("traj_frame", C.c_int32), ("pad2", C.c_int32)]
+
+
+TRACK_DTYPE = np.dtype([("track_id", "<i4"), ("state", "<i4"), ("is_activated", "<i4"), ("class_id", "<i4"), ("start_frame", "<i4"),
+                        ("frame_id", "<i4"), ("tracklet_len", "<i4"), ("pad", "<i4"), ("score", "<f8"), ("tlwh", "<f8", (4,)), ("mean", "<f8", (8,)), ("det_tlbr", "<f8", (4,)), ("traj_frame", "<i4"), ("pad2", "<i4")])
+assert TRACK_DTYPE.itemsize == C.sizeof(TrackRec)
+
+
+class NativeTracker:
+    """Owns one adas_tracker handle (native ByteTrack; association stages on the device)."""
+    MAX_OUT = 1024
+
+    def __init__(self, device=0, track_thresh=0.5, track_buffer=30, match_thresh=0.8, frame_rate=30):
+        self._h = C.c_void_p()
+        check(lib().adas_tracker_create(int(device), C.c_double(track_thresh), int(track_buffer), C.c_double(match_thresh), int(frame_rate),
+                                        C.byref(self._h)))
+        self._out = np.zeros(self.MAX_OUT, TRACK_DTYPE)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().adas_tracker_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib().adas_tracker_reset(self._h))
+
+    def update(self, boxes_xyxy, scores, class_ids) -> np.ndarray:
+        b = as_c(np.asarray(boxes_xyxy, np.float64).reshape(-1, 4), np.float64)
+        s = as_c(scores, np.float64)
+        c = as_c(class_ids, np.int32)
+        n = C.c_int()
+        check(lib().adas_tracker_update(self._h, int(b.shape[0]), _p(b, C.c_double), _p(s, C.c_double), _p(c, C.c_int32), self.MAX_OUT,
+                                        self._out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return self._out[:min(n.value, self.MAX_OUT)].copy()
+
+    def get(self, which: int) -> np.ndarray:
+        n = C.c_int()
+        check(lib().adas_tracker_get(self._h, which, self.MAX_OUT, self._out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return self._out[:min(n.value, self.MAX_OUT)].copy()
+
+    @staticmethod
+    def count() -> int:
+        return int(lib().adas_tracker_count())
 
 
 class Engine:

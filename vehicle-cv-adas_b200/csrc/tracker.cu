@@ -1,0 +1,354 @@
+// tracker.cu -- native ByteTrack state machine (host C++) driving the device association kernels of track.cu.
+//
+// Replaces the per-frame Python of ObjectTracker/byteTrack/byteTracker.py:62-185 (three association stages, births,
+// ageing, list maintenance), dtypes/strack.py (track records, class vote, conversions), dtypes/kalman_filter.py:55-226
+// (constant-velocity filter, float64) and utils.py:9-69 (joint / sub / duplicate removal).  The IoU cost matrices and
+// the exact assignment of every stage run on the device (iou_cost_kernel + lap_kernel, one launch pair and one
+// synchronisation per stage); the 8x8 float64 Kalman algebra and the list bookkeeping are sequential per stream and
+// stay on the host, now without interpreter overhead.
+#include "common.h"
+#include "../../include/adas_b200.h"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <memory>
+#include <utility>
+
+namespace adas {
+int launch_iou_cost(int problems, const double* a, const int32_t* a_off, const double* b, const int32_t* b_off,
+                    const double* det_scores, int fuse, double* cost, const int64_t* cost_off, cudaStream_t st);
+int launch_lap(int problems, const double* cost, const int64_t* cost_off, const int32_t* T, const int32_t* D,
+               const double* thresh, int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off, double* work_v,
+               double* work_minv, int32_t* work_i, cudaStream_t st);
+int lap_max_cols();
+
+enum { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
+static std::atomic<int> g_track_count{0};          // BaseTrack._count: process-global (base_track.py:12,33-36)
+
+struct Track {
+    double tlwh0[4];
+    double mean[8];
+    double cov[64];
+    bool has_kf = false, activated = false;
+    int state = ST_NEW, id = 0, frame = 0, start = 0, cls = 0, tracklet_len = 0;
+    double score = 0.0;
+    double det_tlbr[4] = {0, 0, 0, 0};
+    int traj_frame = 0;
+    std::vector<std::pair<int, int>> votes;     // class-id history in insertion order (dict semantics)
+
+    void tlwh(double* o) const {
+        if (!has_kf) { memcpy(o, tlwh0, 32); return; }
+        o[2] = mean[2] * mean[3]; o[3] = mean[3];
+        o[0] = mean[0] - o[2] / 2; o[1] = mean[1] - o[3] / 2;
+    }
+    void tlbr(double* o) const { tlwh(o); o[2] += o[0]; o[3] += o[1]; }
+    void vote(int c) {                          // strack.py:122-129 (a class seen for the first time after birth starts at 2)
+        bool found = false;
+        for (auto& v : votes) if (v.first == c) { v.second += 1; found = true; break; }
+        if (!found) votes.push_back({c, 2});
+        int best = votes[0].second; cls = votes[0].first;
+        for (auto& v : votes) if (v.second > best) { best = v.second; cls = v.first; }
+    }
+};
+typedef std::shared_ptr<Track> TrackP;
+
+static const double W_POS = 1.0 / 20, W_VEL = 1.0 / 160;
+
+static void xyah_of_tlwh(const double* t, double* z) { z[0] = t[0] + t[2] / 2; z[1] = t[1] + t[3] / 2; z[2] = t[2] / t[3]; z[3] = t[3]; }
+
+static void kf_initiate(Track& t) {                // kalman_filter.py:55-86
+    double z[4];
+    xyah_of_tlwh(t.tlwh0, z);
+    for (int i = 0; i < 4; ++i) { t.mean[i] = z[i]; t.mean[4 + i] = 0.0; }
+    const double h = z[3];
+    const double std_[8] = {2 * W_POS * h, 2 * W_POS * h, 1e-2, 2 * W_POS * h, 10 * W_VEL * h, 10 * W_VEL * h, 1e-5, 10 * W_VEL * h};
+    memset(t.cov, 0, sizeof(t.cov));
+    for (int i = 0; i < 8; ++i) t.cov[i * 9] = std_[i] * std_[i];
+    t.has_kf = true;
+}
+
+static void kf_predict(Track& t) {                 // kalman_filter.py:155-192 with F = [[I, I], [0, I]]
+    if (t.state != ST_TRACKED) t.mean[7] = 0.0;   // strack.py:66-68
+    const double h = t.mean[3];
+    const double sp[4] = {W_POS * h, W_POS * h, 1e-2, W_POS * h}, sv[4] = {W_VEL * h, W_VEL * h, 1e-5, W_VEL * h};
+    for (int i = 0; i < 4; ++i) t.mean[i] += t.mean[4 + i];
+    double fc[64], out[64];
+    for (int i = 0; i < 8; ++i)                   // F * cov : row i += row i+4 for i < 4
+        for (int j = 0; j < 8; ++j) fc[i * 8 + j] = t.cov[i * 8 + j] + (i < 4 ? t.cov[(i + 4) * 8 + j] : 0.0);
+    for (int i = 0; i < 8; ++i)                   // (F cov) * F^T : col j += col j+4 for j < 4
+        for (int j = 0; j < 8; ++j) out[i * 8 + j] = fc[i * 8 + j] + (j < 4 ? fc[i * 8 + j + 4] : 0.0);
+    for (int i = 0; i < 4; ++i) { out[i * 9] += sp[i] * sp[i]; out[(4 + i) * 9] += sv[i] * sv[i]; }
+    memcpy(t.cov, out, sizeof(out));
+}
+
+static void kf_update(Track& t, const double* z) {  // kalman_filter.py:194-226 (project + Cholesky solve)
+    const double h = t.mean[3];
+    const double sd[4] = {W_POS * h, W_POS * h, 1e-1, W_POS * h};
+    double pc[16], L[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) pc[i * 4 + j] = t.cov[i * 8 + j] + (i == j ? sd[i] * sd[i] : 0.0);
+    memset(L, 0, sizeof(L));
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = pc[i * 4 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 4 + k] * L[j * 4 + k];
+            L[i * 4 + j] = (i == j) ? sqrt(s) : s / L[j * 4 + j];
+        }
+    // gain[r][:] solves pc * g = cov[r][0:4]^T for every state row r  (K = cov H^T pc^-1)
+    double K[32];
+    for (int r = 0; r < 8; ++r) {
+        double y[4], g[4];
+        for (int i = 0; i < 4; ++i) { double s = t.cov[r * 8 + i]; for (int k = 0; k < i; ++k) s -= L[i * 4 + k] * y[k]; y[i] = s / L[i * 4 + i]; }
+        for (int i = 3; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 4; ++k) s -= L[k * 4 + i] * g[k]; g[i] = s / L[i * 4 + i]; }
+        for (int i = 0; i < 4; ++i) K[r * 4 + i] = g[i];
+    }
+    double innov[4];
+    for (int i = 0; i < 4; ++i) innov[i] = z[i] - t.mean[i];
+    for (int r = 0; r < 8; ++r) { double s = 0; for (int i = 0; i < 4; ++i) s += innov[i] * K[r * 4 + i]; t.mean[r] += s; }
+    double kp[32];                                 // K * pc
+    for (int r = 0; r < 8; ++r) for (int j = 0; j < 4; ++j) { double s = 0; for (int i = 0; i < 4; ++i) s += K[r * 4 + i] * pc[i * 4 + j]; kp[r * 4 + j] = s; }
+    for (int r = 0; r < 8; ++r) for (int c = 0; c < 8; ++c) { double s = 0; for (int j = 0; j < 4; ++j) s += kp[r * 4 + j] * K[c * 4 + j]; t.cov[r * 8 + c] -= s; }
+}
+
+static double iou_dist(const double* a, const double* b) {   // matching.py:34-53 on the host (duplicate removal only)
+    const double xx1 = std::max(a[0], b[0]), yy1 = std::max(a[1], b[1]), xx2 = std::min(a[2], b[2]), yy2 = std::min(a[3], b[3]);
+    const double w = std::max(0.0, xx2 - xx1), h = std::max(0.0, yy2 - yy1), wh = w * h;
+    return 1.0 - wh / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - wh);
+}
+
+}  // namespace adas
+
+using namespace adas;
+
+struct adas_tracker {
+    int device = 0;
+    double track_thresh = 0.5, match_thresh = 0.8, det_thresh = 0.6;
+    int max_time_lost = 30, frame_id = 0;
+    std::vector<TrackP> tracked, lost, removed;
+    // device scratch (persistent) for the association stages
+    cudaStream_t st = nullptr;
+    size_t cap_boxes = 0, cap_cost = 0;
+    double *d_a = nullptr, *d_b = nullptr, *d_s = nullptr, *d_c = nullptr, *d_th = nullptr, *d_v = nullptr, *d_mv = nullptr;
+    int32_t *d_meta = nullptr, *d_x = nullptr, *d_y = nullptr, *d_wi = nullptr;
+    int64_t* d_co = nullptr;
+    std::vector<double> ha, hb, hs;
+    std::vector<int32_t> hx, hy;
+};
+
+namespace adas {
+
+static int ensure_scratch(adas_tracker* t, size_t nb, size_t nc) {
+    if (t->st == nullptr) {
+        ADAS_CUDA(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+        const size_t wc = (size_t)lap_max_cols() + 1;
+        ADAS_CUDA(cudaMalloc(&t->d_th, 8)); ADAS_CUDA(cudaMalloc(&t->d_v, wc * 8)); ADAS_CUDA(cudaMalloc(&t->d_mv, wc * 8));
+        ADAS_CUDA(cudaMalloc(&t->d_wi, wc * 12)); ADAS_CUDA(cudaMalloc(&t->d_meta, 32)); ADAS_CUDA(cudaMalloc(&t->d_co, 16));
+    }
+    if (nb > t->cap_boxes || nc > t->cap_cost) {
+        cudaFree(t->d_a); cudaFree(t->d_b); cudaFree(t->d_s); cudaFree(t->d_c); cudaFree(t->d_x); cudaFree(t->d_y);
+        t->cap_boxes = std::max<size_t>(256, nb * 2); t->cap_cost = std::max<size_t>(65536, nc * 2);
+        ADAS_CUDA(cudaMalloc(&t->d_a, t->cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&t->d_b, t->cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&t->d_s, t->cap_boxes * 8));
+        ADAS_CUDA(cudaMalloc(&t->d_c, t->cap_cost * 8)); ADAS_CUDA(cudaMalloc(&t->d_x, t->cap_boxes * 4)); ADAS_CUDA(cudaMalloc(&t->d_y, t->cap_boxes * 4));
+    }
+    return 0;
+}
+
+// one association stage on the device: cost = 1 - IoU (optionally fused with the detection scores), exact assignment
+static int associate(adas_tracker* t, const std::vector<TrackP>& trk, const std::vector<TrackP>& det, double thresh, bool fuse,
+                     std::vector<std::pair<int, int>>* matches, std::vector<int>* u_trk, std::vector<int>* u_det) {
+    matches->clear(); u_trk->clear(); u_det->clear();
+    const int T = (int)trk.size(), D = (int)det.size();
+    if (T == 0 || D == 0) {                        // matching.py:21-22
+        for (int i = 0; i < T; ++i) u_trk->push_back(i);
+        for (int j = 0; j < D; ++j) u_det->push_back(j);
+        return 0;
+    }
+    ADAS_CHECK(T + D <= lap_max_cols() && T <= lap_max_cols() / 2, "tracker: association too large (T=%d D=%d)", T, D);
+    if (ensure_scratch(t, (size_t)std::max(T, D), (size_t)T * D)) return 1;
+    t->ha.resize((size_t)T * 4); t->hb.resize((size_t)D * 4); t->hs.resize(D); t->hx.resize(T); t->hy.resize(D);
+    for (int i = 0; i < T; ++i) trk[i]->tlbr(&t->ha[(size_t)i * 4]);
+    for (int j = 0; j < D; ++j) { det[j]->tlbr(&t->hb[(size_t)j * 4]); t->hs[j] = det[j]->score; }
+    const int32_t meta[8] = {0, T, 0, D, T, D, 0, 0};
+    const int64_t co[2] = {0, (int64_t)T * D};
+    ADAS_CUDA(cudaMemcpyAsync(t->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, t->st));
+    ADAS_CUDA(cudaMemcpyAsync(t->d_co, co, sizeof(co), cudaMemcpyHostToDevice, t->st));
+    ADAS_CUDA(cudaMemcpyAsync(t->d_a, t->ha.data(), (size_t)T * 32, cudaMemcpyHostToDevice, t->st));
+    ADAS_CUDA(cudaMemcpyAsync(t->d_b, t->hb.data(), (size_t)D * 32, cudaMemcpyHostToDevice, t->st));
+    if (fuse) ADAS_CUDA(cudaMemcpyAsync(t->d_s, t->hs.data(), (size_t)D * 8, cudaMemcpyHostToDevice, t->st));
+    ADAS_CUDA(cudaMemcpyAsync(t->d_th, &thresh, 8, cudaMemcpyHostToDevice, t->st));
+    if (launch_iou_cost(1, t->d_a, t->d_meta, t->d_b, t->d_meta + 2, fuse ? t->d_s : nullptr, fuse ? 1 : 0, t->d_c, t->d_co, t->st)) return 1;
+    if (launch_lap(1, t->d_c, t->d_co, t->d_meta + 4, t->d_meta + 5, t->d_th, t->d_x, t->d_meta + 6, t->d_y, t->d_meta + 6, t->d_v, t->d_mv, t->d_wi, t->st)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(t->hx.data(), t->d_x, (size_t)T * 4, cudaMemcpyDeviceToHost, t->st));
+    ADAS_CUDA(cudaMemcpyAsync(t->hy.data(), t->d_y, (size_t)D * 4, cudaMemcpyDeviceToHost, t->st));
+    ADAS_CUDA(cudaStreamSynchronize(t->st));
+    for (int i = 0; i < T; ++i) { if (t->hx[i] >= 0) matches->push_back({i, t->hx[i]}); else u_trk->push_back(i); }
+    for (int j = 0; j < D; ++j) if (t->hy[j] < 0) u_det->push_back(j);
+    return 0;
+}
+
+static void hit(adas_tracker* t, Track& tr, const Track& det, std::vector<TrackP>* activated, std::vector<TrackP>* refind, const TrackP& self) {
+    double tl[4], z[4];
+    det.tlwh(tl);
+    xyah_of_tlwh(tl, z);
+    const bool was_tracked = tr.state == ST_TRACKED;
+    kf_update(tr, z);
+    if (was_tracked) { tr.tracklet_len += 1; det.tlbr(tr.det_tlbr); tr.traj_frame = t->frame_id; } else tr.tracklet_len = 0;
+    tr.frame = t->frame_id; tr.state = ST_TRACKED; tr.activated = true; tr.score = det.score;
+    tr.vote(det.cls);
+    (was_tracked ? activated : refind)->push_back(self);
+}
+
+static std::vector<TrackP> joint(const std::vector<TrackP>& a, const std::vector<TrackP>& b) {   // utils.py:9-30
+    std::vector<TrackP> out;
+    std::vector<int> seen;
+    for (const auto* l : {&a, &b})
+        for (const auto& x : *l)
+            if (std::find(seen.begin(), seen.end(), x->id) == seen.end()) { seen.push_back(x->id); out.push_back(x); }
+    return out;
+}
+static std::vector<TrackP> sub(const std::vector<TrackP>& a, const std::vector<TrackP>& b) {     // utils.py:33-51 (dict: last duplicate wins, first position kept)
+    std::vector<TrackP> uniq;
+    for (const auto& x : a) {
+        bool rep = false;
+        for (auto& u : uniq) if (u->id == x->id) { u = x; rep = true; break; }
+        if (!rep) uniq.push_back(x);
+    }
+    std::vector<TrackP> out;
+    for (const auto& x : uniq) {
+        bool drop = false;
+        for (const auto& y : b) if (y->id == x->id) { drop = true; break; }
+        if (!drop) out.push_back(x);
+    }
+    return out;
+}
+
+static void fill_out(const Track& s, adas_track* o) {
+    o->track_id = s.id; o->state = s.state; o->is_activated = s.activated ? 1 : 0; o->class_id = s.cls; o->score = s.score;
+    o->start_frame = s.start; o->frame_id = s.frame; o->tracklet_len = s.tracklet_len;
+    s.tlwh(o->tlwh);
+    if (s.has_kf) memcpy(o->mean, s.mean, 64); else memset(o->mean, 0, 64);
+    memcpy(o->det_tlbr, s.det_tlbr, 32); o->traj_frame = s.traj_frame; o->pad = 0; o->pad2 = 0;
+}
+
+}  // namespace adas
+
+extern "C" {
+
+int adas_tracker_create(int device, double track_thresh, int track_buffer, double match_thresh, int frame_rate, adas_tracker** out) {
+    ADAS_CHECK(out != nullptr, "adas_tracker_create: null argument");
+    adas_tracker* t = new adas_tracker();
+    t->device = device; t->track_thresh = track_thresh; t->match_thresh = match_thresh; t->det_thresh = track_thresh + 0.1;
+    t->max_time_lost = (int)((double)frame_rate / 30.0 * track_buffer);
+    *out = t;
+    return 0;
+}
+
+int adas_tracker_destroy(adas_tracker* t) {
+    if (!t) return 0;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_a); cudaFree(t->d_b); cudaFree(t->d_s); cudaFree(t->d_c); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_th); cudaFree(t->d_v);
+    cudaFree(t->d_mv); cudaFree(t->d_wi); cudaFree(t->d_meta); cudaFree(t->d_co);
+    if (t->st) cudaStreamDestroy(t->st);
+    delete t;
+    return 0;
+}
+
+int adas_tracker_reset(adas_tracker* t) {          // BYTETracker.reset, byteTracker.py:187-200 (also BaseTrack.reset_counter)
+    t->frame_id = 0; t->tracked.clear(); t->lost.clear(); t->removed.clear();
+    g_track_count.store(0);
+    return 0;
+}
+
+int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores, const int32_t* class_ids, int max_out,
+                        adas_track* out, int* n_out) {
+    ADAS_CHECK(t != nullptr && n >= 0, "adas_tracker_update: bad arguments");
+    ADAS_CUDA(cudaSetDevice(t->device));
+    t->frame_id += 1;
+    std::vector<TrackP> activated, refind, lost_now, removed_now, dets, dets2;
+    for (int i = 0; i < n; ++i) {
+        const double s = scores[i];
+        const bool hi = s > t->track_thresh, lo = (s > 0.1) && (s < t->track_thresh);
+        if (!hi && !lo) continue;
+        TrackP d = std::make_shared<Track>();
+        d->tlwh0[0] = boxes_xyxy[i * 4]; d->tlwh0[1] = boxes_xyxy[i * 4 + 1];
+        d->tlwh0[2] = boxes_xyxy[i * 4 + 2] - boxes_xyxy[i * 4]; d->tlwh0[3] = boxes_xyxy[i * 4 + 3] - boxes_xyxy[i * 4 + 1];
+        d->score = s; d->cls = class_ids[i]; d->votes.push_back({class_ids[i], 1});
+        (hi ? dets : dets2).push_back(d);
+    }
+    std::vector<TrackP> unconfirmed, confirmed;
+    for (auto& x : t->tracked) (x->activated ? confirmed : unconfirmed).push_back(x);
+    std::vector<TrackP> pool = joint(confirmed, t->lost);
+    for (auto& x : pool) kf_predict(*x);
+    std::vector<std::pair<int, int>> m;
+    std::vector<int> ut, ud;
+    // stage 1: confirmed + lost vs high-score detections, fused cost
+    if (associate(t, pool, dets, t->match_thresh, true, &m, &ut, &ud)) return 1;
+    for (auto& pr : m) hit(t, *pool[pr.first], *dets[pr.second], &activated, &refind, pool[pr.first]);
+    // stage 2: still-tracked leftovers vs low-score detections, plain IoU
+    std::vector<TrackP> rem;
+    for (int i : ut) if (pool[i]->state == ST_TRACKED) rem.push_back(pool[i]);
+    std::vector<int> ut2, ud2;
+    if (associate(t, rem, dets2, 0.5, false, &m, &ut2, &ud2)) return 1;
+    for (auto& pr : m) hit(t, *rem[pr.first], *dets2[pr.second], &activated, &refind, rem[pr.first]);
+    for (int i : ut2) if (rem[i]->state != ST_LOST) { rem[i]->state = ST_LOST; lost_now.push_back(rem[i]); }
+    // stage 3: unconfirmed vs leftover high detections, fused cost
+    std::vector<TrackP> left;
+    for (int j : ud) left.push_back(dets[j]);
+    std::vector<int> uu, ud3;
+    if (associate(t, unconfirmed, left, 0.7, true, &m, &uu, &ud3)) return 1;
+    for (auto& pr : m) hit(t, *unconfirmed[pr.first], *left[pr.second], &activated, &activated, unconfirmed[pr.first]);
+    for (int i : uu) { unconfirmed[i]->state = ST_REMOVED; removed_now.push_back(unconfirmed[i]); }
+    // births
+    for (int j : ud3) {
+        Track& d = *left[j];
+        if (d.score < t->det_thresh) continue;
+        d.id = g_track_count.fetch_add(1) + 1;
+        kf_initiate(d);
+        d.tracklet_len = 0; d.state = ST_TRACKED; d.activated = (t->frame_id == 1);
+        d.frame = d.start = t->frame_id;
+        activated.push_back(left[j]);
+    }
+    // ageing and list maintenance (byteTracker.py:170-183)
+    for (auto& x : t->lost) if (t->frame_id - x->frame > t->max_time_lost) { x->state = ST_REMOVED; removed_now.push_back(x); }
+    std::vector<TrackP> keep;
+    for (auto& x : t->tracked) if (x->state == ST_TRACKED) keep.push_back(x);
+    t->tracked = joint(joint(keep, activated), refind);
+    t->lost = sub(t->lost, t->tracked);
+    t->lost.insert(t->lost.end(), lost_now.begin(), lost_now.end());
+    t->lost = sub(t->lost, t->removed);
+    t->removed.insert(t->removed.end(), removed_now.begin(), removed_now.end());
+    {   // remove_duplicate_stracks, utils.py:54-69
+        const size_t na = t->tracked.size(), nb = t->lost.size();
+        std::vector<char> da(na, 0), db(nb, 0);
+        std::vector<double> ba(na * 4), bb(nb * 4);
+        for (size_t i = 0; i < na; ++i) t->tracked[i]->tlbr(&ba[i * 4]);
+        for (size_t j = 0; j < nb; ++j) t->lost[j]->tlbr(&bb[j * 4]);
+        for (size_t i = 0; i < na; ++i)
+            for (size_t j = 0; j < nb; ++j)
+                if (iou_dist(&ba[i * 4], &bb[j * 4]) < 0.15) {
+                    const int ta = t->tracked[i]->frame - t->tracked[i]->start, tb = t->lost[j]->frame - t->lost[j]->start;
+                    if (ta > tb) db[j] = 1; else da[i] = 1;
+                }
+        std::vector<TrackP> ra, rb;
+        for (size_t i = 0; i < na; ++i) if (!da[i]) ra.push_back(t->tracked[i]);
+        for (size_t j = 0; j < nb; ++j) if (!db[j]) rb.push_back(t->lost[j]);
+        t->tracked.swap(ra); t->lost.swap(rb);
+    }
+    // removed tracks are never read again: keep only their ids' worth of memory bounded
+    if (t->removed.size() > 4096) t->removed.erase(t->removed.begin(), t->removed.begin() + 2048);
+    int k = 0;
+    for (auto& x : t->tracked) { if (out && k < max_out) fill_out(*x, &out[k]); ++k; }
+    if (n_out) *n_out = k;
+    return 0;
+}
+
+int adas_tracker_get(adas_tracker* t, int which, int max_out, adas_track* out, int* n_out) {
+    const std::vector<TrackP>& l = which == 0 ? t->tracked : (which == 1 ? t->lost : t->removed);
+    int k = 0;
+    for (auto& x : l) { if (out && k < max_out) fill_out(*x, &out[k]); ++k; }
+    if (n_out) *n_out = k;
+    return 0;
+}
+
+int adas_tracker_count(void) { return g_track_count.load(); }
+
+}  // extern "C"

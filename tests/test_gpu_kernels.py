@@ -94,6 +94,31 @@ def test_stem_convs(tmp_path, impl):
 
 
 @pytest.mark.parametrize("impl", [1, 0])
+def test_stem_repack_7x7s2(tmp_path, impl):
+    """UFLD/ResNet stem without a patch matrix: stempack re-layout + 4 vertical GEMM taps == conv2d(7, stride 2, pad 3)."""
+    rng = np.random.default_rng(11)
+    for (B, H, W) in ((2, 32, 64), (1, 64, 160)):
+        pb = plan.PlanBuilder(plan.MODEL_UFLDV2, 3, H, W)
+        w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+        b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+        out = pb.stem7x7s2(pb.image, w, b, plan.ACT_RELU)
+        path = str(tmp_path / f"stem_{impl}_{H}.b200w")
+        pb.write(path)
+        eng = _capi.Engine(path, 0, max_batch=B, conv_impl=impl)
+        x = rng.standard_normal((B, 3, H, W)).astype(np.float32)
+        eng.write_buffer(pb.image.buf, to_padded(x, 4))
+        for _ in range(3):
+            eng.run(B)
+        got_buf = eng.read_buffer(out.buf, B)
+        got = from_padded(got_buf, B, H // 2, W // 2, 0, 64)
+        ref = F.relu(F.conv2d(torch.from_numpy(x).half().float(), torch.from_numpy(w).half().float(), torch.from_numpy(b), stride=2, padding=3)).numpy()
+        err = float(np.abs(got - ref).max()) / max(1.0, float(np.abs(ref).max()))
+        assert err < 4e-3, (impl, H, err)
+        assert halo_is_zero(got_buf, B, H // 2, W // 2)
+        eng.close()
+
+
+@pytest.mark.parametrize("impl", [1, 0])
 def test_fc_swap_ab(tmp_path, impl):
     rng = np.random.default_rng(3)
     for (B, K, N, act) in ((3, 4992, 2048, 2), (8, 2048, 9128, 0), (1, 256, 136, 0)):

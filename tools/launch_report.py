@@ -19,7 +19,7 @@ out = []
 for (typ, p, f), (name, grid, us) in zip(pb.ops, rows):
     if typ == 1:
         a_buf, a_coff, Kc, ntaps, wt, bt, N, act, rb, rc, rp, ob, oc, masked, tr, BN = p[:16]
-        M = B * pb.buffers[a_buf][0] if not tr else N
+        M = B * pb.buffers[ob if p[16] else a_buf][0] if not tr else N
         Nn = N if not tr else B
         out.append((us, M, Nn, Kc * ntaps, ntaps, grid, 2 * M * Nn * Kc * ntaps / us / 1e6))
 print("  GEMM launches by time: us, M, N, K, taps, grid, TFLOP/s (incl. halo rows)")

@@ -253,6 +253,44 @@ int launch_nchw_to_padded(const float* in, int B, int C, int H, int W, __half* o
     return 0;
 }
 
+// ---- 7x7 stride-2 stem re-layout ---------------------------------------------------------------------
+// Q[b][yy = j][xo+1][p*32 + kx*4 + c] = img[b][2j-1+p][2xo+kx-3][c]   (j = 0 .. Ho, p = 0,1, kx = 0..6, c = 0..3; kx = 7 is zero)
+// written on the padded grid of the stem OUTPUT (Ho x Wo): row yy = j holds the input-row pair (2j-1, 2j).  One thread writes the
+// 16 bytes of two horizontal taps (kx, kx+1) of one pair half; the image (4 MB per frame) stays in L2 while it is re-read.
+__global__ void stempack_kernel(const __half* __restrict__ img, int B, int H, int W, __half* __restrict__ q) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long total = (long long)B * (Ho + 1) * Wo * 8;     // 8 chunks of 16 B per Q pixel
+    const int Hp = H + 2, Wp = W + 2, Hop = Ho + 2, Wop = Wo + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i & 7);                 // chunk: p = ch >> 2, kx pair = (ch & 3) * 2
+        long long t = i >> 3;
+        const int xo = (int)(t % Wo); t /= Wo;
+        const int j = (int)(t % (Ho + 1));
+        const int b = (int)(t / (Ho + 1));
+        const int pp = ch >> 2, kx0 = (ch & 3) * 2;
+        const int y = 2 * j - 1 + pp;
+        uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+        if (y >= 0 && y < H) {
+            const int x0 = 2 * xo + kx0 - 3, x1 = x0 + 1;
+            const __half* row = img + ((size_t)b * Hp + (y + 1)) * Wp * 4;
+            if (x0 >= 0 && x0 < W) v0 = *reinterpret_cast<const uint2*>(row + (size_t)(x0 + 1) * 4);
+            if (kx0 + 1 < 7 && x1 >= 0 && x1 < W) v1 = *reinterpret_cast<const uint2*>(row + (size_t)(x1 + 1) * 4);
+        }
+        const size_t orow = ((size_t)b * Hop + j) * Wop + (xo + 1);
+        *reinterpret_cast<uint4*>(q + orow * 64 + ch * 8) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+    }
+}
+
+int launch_stempack(const __half* img, int B, int H, int W, __half* q, cudaStream_t st) {
+    const long long total = (long long)B * (H / 2 + 1) * (W / 2) * 8;
+    int blocks = grid_for(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    stempack_kernel<<<blocks, 256, 0, st>>>(img, B, H, W, q);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_zero_rows(__half* buf, int ld, int C, int row0, int nrows, cudaStream_t st) {
     ADAS_CUDA(cudaMemset2DAsync(buf + (size_t)row0 * ld, (size_t)ld * 2, 0, (size_t)C * 2, nrows, st));
     return 0;

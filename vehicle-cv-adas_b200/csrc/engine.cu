@@ -128,7 +128,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 const PlanBuffer& ob = e->bufs[out_buf];
                 ADAS_CHECK(ab.dtype == 0, "op %zu: GEMM input buffer must be fp16", oi);
                 ADAS_CHECK(Kc % 8 == 0 && a_coff % 8 == 0 && ab.C % 8 == 0, "op %zu: K alignment", oi);
-                ADAS_CHECK(ntaps == 1 || (ntaps == 9 && Kc % 64 == 0 && ab.W > 0), "op %zu: tap mode needs Cin %% 64 == 0", oi);
+                ADAS_CHECK(ntaps == 1 || ((ntaps == 9 || ntaps == 4) && Kc % 64 == 0 && ab.W > 0), "op %zu: tap mode needs Cin %% 64 == 0", oi);
                 ADAS_CHECK(!s2 || (Kc % 64 == 0 && ab.W > 0 && ob.W > 0 && !transposed), "op %zu: stride-2 mode needs Cin %% 64 == 0 on padded grids", oi);
                 GemmParams g;
                 memset(&g, 0, sizeof(g));
@@ -282,6 +282,16 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 const int in_ld = (int)ib.C, H = (int)ib.H, W = (int)ib.W, C = p[2], out_ld = (int)ob.C;
                 ADAS_CHECK((int)ob.H == 2 * H && (int)ob.W == 2 * W, "op %zu: upsample geometry", oi);
                 prog->steps.push_back([=](cudaStream_t st) { return launch_upsample2x(in, in_ld, batch, H, W, C, out, out_ld, st); });
+                break;
+            }
+            case OP_STEMPACK: {
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[1]];
+                ADAS_CHECK(ib.C == 4 && ob.C == 64 && ob.H * 2 == ib.H && ob.W * 2 == ib.W, "op %zu: stem pack geometry", oi);
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr);
+                __half* out = static_cast<__half*>(e->dbufs[p[1]].ptr);
+                const int H = (int)ib.H, W = (int)ib.W;
+                prog->steps.push_back([=](cudaStream_t st) { return launch_stempack(in, batch, H, W, out, st); });
                 break;
             }
             case OP_LAYERNORM: {

@@ -513,6 +513,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     } else {
                         int shift = 0;
                         if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
+                        else if (p.ntaps == 4) shift = (grp - 2) * p.Wp;          // stem: row pairs yo-1 .. yo+2 (plan.py stem7x7s2)
                         for (int mt = 0; mt < g.MT; ++mt) {
                             if (g_pair) tma_load_2d_pair(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
                             else tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
@@ -1007,6 +1008,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     for (int tap = 0; tap < p.ntaps; ++tap) {
         int shift = 0;
         if (p.ntaps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+        else if (p.ntaps == 4) shift = (tap - 2) * p.Wp;
         long ar = (long)row + shift;
         if (p.s2) {
             // out row -> (b, yo, xo); input pixel (2*yo+dy, 2*xo+dx) in the input's padded grid

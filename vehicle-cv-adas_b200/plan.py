@@ -31,7 +31,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 MODEL_YOLOV8, MODEL_YOLOV5, MODEL_UFLDV2 = 0, 1, 2
-OP_GEMM, OP_IM2COL, OP_MAXPOOL, OP_UPSAMPLE2X, OP_LAYERNORM = 1, 2, 3, 4, 5
+OP_GEMM, OP_IM2COL, OP_MAXPOOL, OP_UPSAMPLE2X, OP_LAYERNORM, OP_STEMPACK = 1, 2, 3, 4, 5, 6
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 PLAN_VERSION = 1
 
@@ -241,6 +241,29 @@ class PlanBuilder:
         self._op(OP_GEMM, [a.buf, a.coff, Kc, ntaps, w_t, bias_t, n_store, act, res_buf, res_coff, 1 if res_pre_act else 0,
                            out.buf, out.coff, 1, 0, 0, s2])
         return View(out.buf, out.coff, cout, Ho, Wo)
+
+    def stem7x7s2(self, x: View, w: np.ndarray, b: np.ndarray, act: int) -> View:
+        """7x7 stride-2 pad-3 conv on the C=4 image without a patch matrix: the image is re-laid out once as
+        Q[j][xo][p*32 + kx*4 + c] = img[2j-1+p][2xo+kx-3][c] (row PAIRS x the 7 horizontal taps = 64 channels) on the
+        OUTPUT's padded grid, which turns the conv into 4 vertically shifted GEMM taps of K = 64 (rows yo-1 .. yo+2)."""
+        cout, cin_real = int(w.shape[0]), int(w.shape[1])
+        assert w.shape[2:] == (7, 7) and x.C == 4 and cin_real <= 4 and x.H % 2 == 0 and x.W % 2 == 0
+        Ho, Wo = x.H // 2, x.W // 2
+        self.flops_per_img += 2 * Ho * Wo * cout * cin_real * 49
+        q = self.new_padded(Ho, Wo, 64)
+        self._op(OP_STEMPACK, [x.buf, q.buf])
+        wq = np.zeros((cout, 4, 2, 8, 4), np.float32)             # [n][t][p][kx(7 used of 8)][c]
+        for t in range(4):
+            for pp in range(2):
+                ky = 2 * t + pp
+                if ky < 7:
+                    wq[:, t, pp, :7, :cin_real] = np.transpose(w[:, :, ky, :], (0, 2, 1))
+        out = self.new_padded(Ho, Wo, (cout + 7) // 8 * 8)
+        w_t = self.tensor(wq.reshape(cout, 256).astype(np.float16))
+        bias_t = self.tensor(b.astype(np.float32))
+        # ntaps = 4 selects the vertical tap table (row shifts -2, -1, 0, +1 padded rows)
+        self._op(OP_GEMM, [q.buf, 0, 64, 4, w_t, bias_t, cout, act, -1, 0, 0, out.buf, 0, 1, 0, 0, 0])
+        return View(out.buf, 0, cout, Ho, Wo)
 
     def maxpool(self, x: View, k: int, s: int, p: int, out: Optional[View] = None) -> View:
         Ho = (x.H + 2 * p - k) // s + 1
@@ -483,7 +506,10 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg: dict = UFLD_CULANE
     pb = PlanBuilder(MODEL_UFLDV2, 3, in_h, in_w)
     W = weights
     w, b = W.conv_bn("model", 64, 3, 7, BN_EPS_TV, conv_key="conv1", bn_key="bn1")
-    x = pb.conv(pb.image, w, b, 7, 2, ACT_RELU, pad=3)
+    if os.environ.get("ADAS_B200_STEMPACK", "1") != "0":
+        x = pb.stem7x7s2(pb.image, w, b, ACT_RELU)
+    else:
+        x = pb.conv(pb.image, w, b, 7, 2, ACT_RELU, pad=3)
     x = pb.maxpool(x, 3, 2, 1)
     cin = 64
     for li, (n, cout) in enumerate(zip(blocks, (64, 128, 256, 512)), start=1):

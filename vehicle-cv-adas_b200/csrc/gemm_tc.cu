@@ -390,6 +390,7 @@ struct GemmV2 {
     int use_base_offset;
     int pair;        // 1: cta_group::2 -- the two CTAs of a cluster run ONE M=256 MMA per step, each staging half of the weight tile
     int mc;          // 1: CTA pairs (cluster 2x1x1) on adjacent M tiles share every weight tile through TMA multicast
+    int pdl;         // 1: launched with programmatic stream serialisation (griddepcontrol in the kernel)
     int work_items;  // scheduler items: tiles, or tile pairs when mc
 };
 
@@ -453,6 +454,13 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (cl2) cluster_sync_all();          // peer barriers are initialised before any multicast / remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_holder;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+    // tail of the previous kernel in the stream; its results may only be touched after this wait.  The next kernel is
+    // allowed to start its own prologue as soon as SMs free up.
+    if (g.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -755,6 +763,7 @@ int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
     g->total_tiles = g->n_tiles * g->m_tiles;
     g->mc = (p.mc_hint == 1 && !p.s2 && g->m_tiles >= 2) ? 1 : 0;
     g->pair = want_pair;
+    g->pdl = 0;
     g->work_items = (g->mc | g->pair) ? g->n_tiles * ((g->m_tiles + 1) / 2) : g->total_tiles;
     const char* bo = getenv("ADAS_B200_BASEOFF");
     g->use_base_offset = (bo && bo[0] == '1');   // measured on B200: the swizzle phase follows the absolute smem address, the field stays 0
@@ -784,6 +793,25 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         attr = true;
     }
     const int smem = g.p.stages * g.stage_bytes + 1024;
+    static int pdl = -1;
+    if (pdl < 0) { const char* pe = getenv("ADAS_B200_PDL"); pdl = (pe && pe[0] == '0') ? 0 : 1; }
+    if (pdl && !(g.mc | g.pair)) {
+        GemmV2 gp = g;
+        gp.pdl = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g.total_tiles < g_num_sms ? g.total_tiles : g_num_sms, 1, 1);
+        cfg.blockDim = dim3(V2_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr1;
+        attr1.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr1.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr1;
+        cfg.numAttrs = 1;
+        ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false>, tmA, tmB, gp));
+        count_launch();
+        return 0;
+    }
     if (g.mc | g.pair) {
         const int pairs_max = g_num_sms / 2;
         const int pairs = g.work_items < pairs_max ? g.work_items : pairs_max;

@@ -140,7 +140,7 @@ def run_b200(args):
     pipe = AdasPipeline(plans["yolov8"][0], plans["ufldv2"][0], device=local, batch=B, box_score=BOX_SCORE, box_nms_iou=NMS_IOU, max_det=MAX_DET)
 
     # one stream per rank; frames differ per step (pool larger than L2: 24 batches x 22 MB = 530 MB >> 126 MB)
-    pool_batches = 24
+    pool_batches = max(6, min(24, 192 // B))
     stream = synth_stream(1000 + rank, B * 4)
     host_pool = torch.empty((pool_batches, B, FRAME_H, FRAME_W, 3), dtype=torch.uint8).pin_memory()
     hp = host_pool.numpy()

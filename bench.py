@@ -83,7 +83,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -261,7 +261,7 @@ def run_b200(args):
             "host_tracker_ms_per_step": round(1e3 * getattr(pipe, "track_seconds", 0.0) / max(1, getattr(pipe, "track_batches", 1)), 3),
             "tracks_alive": len(pipe.tracker.tracked_stracks),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_v2_kernel (tcgen05 implicit-GEMM conv/FC, persistent)", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; GEMM launches timed alone, of measured)" if peaks else "fallback 1590 (of fallback)",
                          "launches_per_step": n_y + n_u, "avg_launch_us": round(1e3 * (ms_y + ms_u) / (n_y + n_u), 2),

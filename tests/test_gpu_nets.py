@@ -191,3 +191,32 @@ def test_bytetracker_matches_reference_golden(golden_dir, impl):
         assert got.shape == gold.shape, (seed, got.shape, gold.shape)
         assert np.array_equal(got[:, [0, 1, 2, 3, 9]], gold[:, [0, 1, 2, 3, 9]])      # frame, track id, activation, state, class: exact
         assert np.allclose(got[:, 4:9], gold[:, 4:9], rtol=0, atol=1e-6)              # Kalman boxes (fp64) and scores
+
+
+def test_detect_pair_concurrent_streams_equal_separate_calls():
+    """adas_detect_pair enqueues both networks on their own streams before waiting for either; the results must be bit-identical
+    to the two stand-alone calls (host frames, and frames already resident on the device), over repeated graph replays."""
+    ypath, _, _ = cached_plan("yolov8", scale="l")
+    upath, _, _ = cached_plan("ufldv2", backbone="18")
+    ye = _capi.Engine(ypath, 0, max_batch=3)
+    ue = _capi.Engine(upath, 0, max_batch=3)
+    frames = np.stack([synth.frame(s) for s in (21, 22, 23)])
+    y_ref = ye.yolo_detect(frames, 0.4, 0.45)
+    u_ref = ue.ufld_detect(frames)
+    dev = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
+    for rep in range(4):         # eager -> capture -> replay -> replay
+        on_dev = rep % 2 == 1
+        y, u = _capi.detect_pair(ye, ue, dev.data_ptr() if on_dev else frames, 0.4, 0.45, 300, on_dev, (3, 720, 1280))
+        n = y[4]
+        assert np.array_equal(n, y_ref[4]) and np.array_equal(y[5], y_ref[5])
+        for b in range(3):
+            for k in range(4):
+                assert np.array_equal(y[k][b, :n[b]], y_ref[k][b, :n[b]])
+        assert np.array_equal(u[1], u_ref[1]) and np.array_equal(u[2], u_ref[2])
+        for b in range(3):
+            for l in range(4):
+                assert np.array_equal(u[0][b, l, :u[1][b, l]], u_ref[0][b, l, :u[1][b, l]])
+    assert int(y_ref[4].sum()) > 0
+    ye.close()
+    ue.close()

@@ -83,6 +83,8 @@ struct adas_engine {
     double* d_col_anchor = nullptr;
     int32_t* d_pts = nullptr; int32_t* d_npts = nullptr; uint8_t* d_status = nullptr; double* d_coords = nullptr;
     int ufld_max_pts = 0;
+    std::vector<int32_t> h_ncand;
+    cudaEvent_t ev_frames = nullptr;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -387,24 +389,32 @@ static void free_yolo_post(YoloPostBufs* w) {
     memset(w, 0, sizeof(*w));
 }
 
-static int copy_yolo_results(const YoloPostBufs& w, int batch, int max_det, float* boxes, float* scores, int32_t* cls, int32_t* idx,
-                             int32_t* counts, int32_t* n_cand, cudaStream_t st) {
+static int copy_yolo_results_enqueue(const YoloPostBufs& w, int batch, int max_det, float* boxes, float* scores, int32_t* cls, int32_t* idx,
+                                     int32_t* counts, int32_t* nc_host, cudaStream_t st) {
     ADAS_CUDA(cudaMemcpyAsync(boxes, w.out_box, (size_t)batch * max_det * 16, cudaMemcpyDeviceToHost, st));
     ADAS_CUDA(cudaMemcpyAsync(scores, w.out_score, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
     ADAS_CUDA(cudaMemcpyAsync(cls, w.out_cls, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
     ADAS_CUDA(cudaMemcpyAsync(idx, w.out_idx, (size_t)batch * max_det * 4, cudaMemcpyDeviceToHost, st));
     ADAS_CUDA(cudaMemcpyAsync(counts, w.out_count, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-    std::vector<int32_t> nc(batch);
-    ADAS_CUDA(cudaMemcpyAsync(nc.data(), w.n_cand, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    ADAS_CUDA(cudaMemcpyAsync(nc_host, w.n_cand, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+static int copy_yolo_results_finish(const YoloPostBufs& w, int batch, int max_det, int32_t* counts, int32_t* n_cand, const int32_t* nc_host,
+                                    cudaStream_t st) {
     ADAS_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < batch; ++b) {
-        if (n_cand) n_cand[b] = nc[b];
-        ADAS_CHECK(nc[b] <= w.cap, "frame %d: %d candidates exceed the device NMS capacity %d (raise box_score)", b, nc[b], w.cap);
+        if (n_cand) n_cand[b] = nc_host[b];
+        ADAS_CHECK(nc_host[b] <= w.cap, "frame %d: %d candidates exceed the device NMS capacity %d (raise box_score)", b, nc_host[b], w.cap);
         if (counts[b] > max_det) counts[b] = max_det;
     }
     return 0;
 }
-
+static int copy_yolo_results(const YoloPostBufs& w, int batch, int max_det, float* boxes, float* scores, int32_t* cls, int32_t* idx,
+                             int32_t* counts, int32_t* n_cand, cudaStream_t st) {
+    std::vector<int32_t> nc(batch);
+    if (copy_yolo_results_enqueue(w, batch, max_det, boxes, scores, cls, idx, counts, nc.data(), st)) return 1;
+    return copy_yolo_results_finish(w, batch, max_det, counts, n_cand, nc.data(), st);
+}
 static void ufld_lut_host(float* lut) {
     // ultrafastLaneDetectorV2.py:105-108,112 under numpy promotion rules: `img / 255.0` stays float32 (python scalar is
     // weak), `- mean` / `/ std` with python lists promote to float64, the final astype rounds once to float32.
@@ -515,6 +525,7 @@ int adas_engine_destroy(adas_engine* e) {
     for (auto& b : e->dbufs) cudaFree(b.ptr);
     cudaFree(e->d_blob); cudaFree(e->d_input); cudaFree(e->d_frames); cudaFree(e->d_raw); cudaFree(e->d_lut);
     cudaFree(e->d_row_anchor); cudaFree(e->d_col_anchor); cudaFree(e->d_pts); cudaFree(e->d_npts); cudaFree(e->d_status); cudaFree(e->d_coords);
+    if (e->ev_frames) cudaEventDestroy(e->ev_frames);
     if (e->yp.flags) free_yolo_post(&e->yp);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -699,9 +710,63 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
 int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames, int frames_on_device, int batch, int H, int W, double box_score,
                      double nms_iou, int max_det, float* boxes_xywh, float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts,
                      int32_t* n_candidates, int32_t* pts, int32_t* npts, uint8_t* status) {
-    if (adas_yolo_detect(yolo, frames, frames_on_device, batch, H, W, box_score, nms_iou, max_det, boxes_xywh, scores, class_ids, cand_index, counts,
-                         n_candidates)) return 1;
-    return adas_ufld_detect(ufld, frames, frames_on_device, batch, H, W, pts, npts, status, nullptr);
+    static int conc = -1;
+    if (conc < 0) { const char* c = getenv("ADAS_B200_CONCURRENT"); conc = (c && c[0] == '0') ? 0 : 1; }
+    if (!conc || yolo->device != ufld->device) {
+        if (adas_yolo_detect(yolo, frames, frames_on_device, batch, H, W, box_score, nms_iou, max_det, boxes_xywh, scores, class_ids, cand_index, counts,
+                             n_candidates)) return 1;
+        return adas_ufld_detect(ufld, frames, frames_on_device, batch, H, W, pts, npts, status, nullptr);
+    }
+    // concurrent variant: both networks are enqueued on their own streams before either is waited for, so the tail waves of one
+    // network's kernels can be back-filled by the other's
+    adas_engine* e = yolo;
+    ADAS_CHECK(batch >= 1 && batch <= e->max_batch && batch <= ufld->max_batch, "batch out of range");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
+    if (e->yp.flags == nullptr || e->yp_max_det != max_det) {
+        if (e->yp.flags) free_yolo_post(&e->yp);
+        if (alloc_yolo_post(&e->yp, e->max_batch, A, max_det)) return 1;
+        e->yp_max_det = max_det;
+    }
+    e->h_ncand.resize(batch);
+    if (!frames_on_device) {      // one upload on the object stream; the lane stream waits for it
+        const uint8_t* dfr = nullptr;
+        if (stage_frames(e, frames, 0, batch, H, W, &dfr)) return 1;
+        if (!e->ev_frames) ADAS_CUDA(cudaEventCreateWithFlags(&e->ev_frames, cudaEventDisableTiming));
+        ADAS_CUDA(cudaEventRecord(e->ev_frames, e->stream));
+        ADAS_CUDA(cudaStreamWaitEvent(ufld->stream, e->ev_frames, 0));
+        frames = dfr;
+    }
+    const LetterboxGeom g = letterbox_geom(H, W, (int)e->hdr.in_h, (int)e->hdr.in_w);
+    if (launch_yolo_pre(frames, batch, g, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr, e->stream)) return 1;
+    {
+        adas_engine* u = ufld;
+        const int in_h = (int)u->hdr.in_h, in_w = (int)u->hdr.in_w;
+        const int resize_h = (int)((double)in_h / 0.6);
+        if (launch_ufld_pre(frames, batch, H, W, in_h, in_w, resize_h, u->d_lut, static_cast<__half*>(u->dbufs[0].ptr), (int)u->bufs[0].C, nullptr,
+                            u->stream)) return 1;
+    }
+    if (run_plan(e, batch)) return 1;
+    if (run_plan(ufld, batch)) return 1;
+    if (head_decode(e, batch)) return 1;
+    if (launch_yolo_post(e->d_raw, (int)e->hdr.model_kind, batch, A, nc, g, box_score, nms_iou, max_det, e->yp, e->stream)) return 1;
+    if (copy_yolo_results_enqueue(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, e->h_ncand.data(), e->stream)) return 1;
+    {
+        adas_engine* u = ufld;
+        const uint32_t* m = u->hdr.meta;
+        UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
+        const PlanOutput& o = u->outs[0];
+        const float* heads = static_cast<const float*>(u->dbufs[o.buffer].ptr) + o.coff;
+        const int mp = u->ufld_max_pts;
+        if (launch_ufld_post(heads, (int)u->bufs[o.buffer].C, batch, d, W, H, u->d_row_anchor, u->d_col_anchor, u->d_pts, u->d_npts, u->d_status, nullptr, mp,
+                             u->stream)) return 1;
+        ADAS_CUDA(cudaMemcpyAsync(pts, u->d_pts, (size_t)batch * 4 * mp * 2 * 4, cudaMemcpyDeviceToHost, u->stream));
+        ADAS_CUDA(cudaMemcpyAsync(npts, u->d_npts, (size_t)batch * 4 * 4, cudaMemcpyDeviceToHost, u->stream));
+        ADAS_CUDA(cudaMemcpyAsync(status, u->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, u->stream));
+    }
+    if (copy_yolo_results_finish(e->yp, batch, max_det, counts, n_candidates, e->h_ncand.data(), e->stream)) return 1;
+    ADAS_CUDA(cudaStreamSynchronize(ufld->stream));
+    return 0;
 }
 
 int adas_ufld_postprocess(int device, const float* heads_host, int batch, int ngr, int ncr, int ngc, int ncc, int nl, int img_w, int img_h,

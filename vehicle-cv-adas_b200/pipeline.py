@@ -2,9 +2,11 @@
 
 demo.py does, per frame and strictly in sequence: `objectDetector.DetectFrame` (269) -> `objectTracker.update` (272-277)
 -> `laneDetector.DetectFrame` (280) -> analytics/drawing.  Here one step takes a batch of consecutive frames of one
-stream:  a worker thread drives the object and lane networks back to back (the ctypes calls release the GIL; running
-the two persistent-kernel streams concurrently was measured SLOWER on B200 -- 10.0 vs 7.0 ms per 8-frame step -- because
-every conv kernel already fills all 148 SMs), while the host thread runs the ByteTrack updates of the PREVIOUS batch:
+stream:  a worker thread makes ONE library call (`adas_detect_pair`) that enqueues the object network and the lane network
+on their own CUDA streams before waiting for either -- the tail waves of one network's persistent conv kernels are
+back-filled by the other's (measured 3.96 vs 4.35 ms per 8-frame step; driving the two streams from two Python threads
+instead was slower, the interpreter lock serialises the launches) -- while the host thread runs the ByteTrack updates of
+the PREVIOUS batch:
 the tracker is sequential in time per stream, so it pipelines one batch behind the detectors.  Per-frame
 results are identical to calling the three detectors frame by frame.
 """

@@ -210,16 +210,21 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     } else if (e->autotune && !transposed && p[15] <= 0) {
                         // measure the modelled top candidates on the device once per (op, batch); every candidate accumulates in the
                         // same K order, so the choice never changes results
-                        int cBN[6], cMT[6];
-                        const int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 6, cBN, cMT);
+                        int cBN[12], cMT[12], cPair[12];
+                        int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 6, cBN, cMT);
+                        for (int k = 0; k < nc; ++k) cPair[k] = (e->mc_mode == 1 || e->mc_mode == 2) ? e->mc_mode : 0;
+                        if (e->mc_mode == 3) {
+                            const int np = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 4, cBN + nc, cMT + nc, 1);
+                            for (int k = 0; k < np; ++k) cPair[nc + k] = 2;
+                            nc += np;
+                        }
                         float best_ms = 1e30f;
                         cudaEvent_t ev0, ev1;
                         ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1));
-                        for (int cj = 0; cj < nc * (e->mc_mode == 3 ? 2 : 1); ++cj) {
-                            const int ci = cj % nc;
+                        for (int ci = 0; ci < nc; ++ci) {
                             GemmParams gc = g;
                             gc.BN = cBN[ci]; gc.mt_hint = cMT[ci];
-                            gc.mc_hint = e->mc_mode == 3 ? (cj >= nc ? 2 : 0) : e->mc_mode;
+                            gc.mc_hint = cPair[ci];
                             void* cand = nullptr;
                             if (gemm_tc_v2_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &cand)) continue;
                             int rc = gemm_tc_v2_run(cand, e->stream);
@@ -231,6 +236,9 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                             }
                             float ms = 1e30f;
                             if (!rc) cudaEventElapsedTime(&ms, ev0, ev1);
+                            static const bool at_log = getenv("ADAS_B200_AT_LOG") != nullptr;
+                            if (at_log) fprintf(stderr, "[autotune] op %zu M=%d N=%d K=%d taps=%d BN=%d mt=%d pair=%d : %.1f us\n", oi, g.M, g.N, Kc * ntaps, ntaps,
+                                                gc.BN, gc.mt_hint == 1 ? 1 : (gc.BN <= 128 ? 2 : 1), gc.mc_hint, rc ? -1.0 : ms * 1000.0 / 3.0);
                             if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_tc_v2_free(opaque); opaque = cand; }
                             else gemm_tc_v2_free(cand);
                         }

@@ -435,7 +435,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), (V2_THREADS - 64) * (g_pair ? 2 : 1));   // pair: both CTAs' epilogues drain the leader's MMA
+            mbar_init(smem_u32(&tempty_bar[s]), ((V2_THREADS - 64) / 32) * (g_pair ? 2 : 1));   // one arrive per epilogue warp; pair: both CTAs' epilogues drain the leader's MMA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -462,7 +462,9 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
 
-    if (warp_idx == 0) {
+    if (p.dbg & 64) {
+        // DEBUG: launch skeleton only (prologue + dependency wait + teardown)
+    } else if (warp_idx == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
             const uint32_t tx_bytes = p.s2 ? (uint32_t)(p.s2_bw * p.s2_bh * BK * 2 + p.BN * BK * 2)
@@ -720,8 +722,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             tcgen05_fence_before();
-            if (g_pair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA waits for both epilogues
-            else mbar_arrive(smem_u32(&tempty_bar[as]));      // this thread is done reading accumulator stage `as`
+            __syncwarp();
+            if (lane == 0) {
+                if (g_pair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA waits for both epilogues
+                else mbar_arrive(smem_u32(&tempty_bar[as]));      // this warp is done reading accumulator stage `as`
+            }
         }
     }
 
@@ -820,12 +825,16 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         cfg.blockDim = dim3(V2_THREADS, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr1;
-        attr1.id = cudaLaunchAttributeClusterDimension;
-        attr1.val.clusterDim.x = 2; attr1.val.clusterDim.y = 1; attr1.val.clusterDim.z = 1;
-        cfg.attrs = &attr1;
-        cfg.numAttrs = 1;
-        ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<true>, tmA, tmB, g));
+        cudaLaunchAttribute attrs[2];
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+        attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = pdl ? 2 : 1;
+        GemmV2 gp = g;
+        gp.pdl = pdl ? 1 : 0;
+        ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<true>, tmA, tmB, gp));
         count_launch();
         return 0;
     }
@@ -840,7 +849,7 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 // Per-layer tile choice.  Measured on B200 (profiles/r01_gemm_analysis.md): one SM ingests ~32 operand bytes per
 // clock from L2 while its tensor pipe retires 4096 MACs per clock, so a tile is modelled by max(operand bytes / 32,
 // MMA clocks, epilogue clocks) and layers are charged whole waves of 148 persistent CTAs.
-int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out) {
+int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out, int pair) {
     // (the multicast on/off variants of each returned candidate are tried by the autotuner in engine.cu)
     const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
     struct C { double t; int BN, mt; } list[24];
@@ -860,15 +869,17 @@ int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_
             GemmParams p;
             memset(&p, 0, sizeof(p));
             p.M = M; p.N = N; p.Kc = Kc; p.ntaps = ntaps; p.kpt = kpt; p.BN = BN; p.mt_hint = mt == 1 ? 1 : 0;
+            p.mc_hint = pair ? 2 : 0;
+            if (pair && BN % 32 != 0) continue;
             GemmV2 g;
             if (gemm_tc_v2_config(p, &g)) continue;
             const double tiles = (double)g.total_tiles;
             const double ksteps = (g.slab ? 3.0 : (double)ntaps) * kpt;
-            const double bytes = ksteps * (g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + (g.slab ? 3 : 1) * BN * 128.0);
+            const double bytes = ksteps * (g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + (g.slab ? 3 : 1) * (pair ? BN / 2 : BN) * 128.0);
             const double mma = (double)g.MT * ntaps * kpt * 2.0 * BN;
             const double epi = (double)g.MT * 128.0 * BN * 0.55;
             const double per_tile = fmax(fmax(bytes / 32.0, mma), epi) + 600.0;
-            const double waves = ceil(tiles / 148.0);
+            const double waves = ceil((pair ? 2.0 * g.work_items : tiles) / 148.0);
             const double t = waves * per_tile + epi * 0.5 + 2500.0;
             if (n < 24) { list[n].t = t; list[n].BN = BN; list[n].mt = mt; ++n; }
         }

@@ -54,7 +54,7 @@ struct GemmParams {
     int res_ld;     // row stride of res, elements; NEGATIVE = add the residual before the activation (ResNet)
     int mask_H, mask_W;  // > 0: only rows in the interior of the padded (H+2)x(W+2) grid are stored
     int dbg;        // debug switches (ADAS_B200_DBG), 0 in production
-    int mt_hint;    // v2 kernel: 1 forces single 128-row sub-tiles (more CTAs for small layers), 0 = auto
+    int mt_hint;    // v2 kernel: number of 128-row sub-tiles per CTA tile (1..4; they share each weight tile), 0 = auto
     int mc_hint;    // v2 kernel: 1 = CTA pairs share weight tiles via TMA multicast (cluster 2x1x1); 2 = cta_group::2 MMA pairs
     // stride-2 convs (3x3 pad 1, or 1x1) read the input through a 4-D TMA map with traversal stride 2: an M tile is a
     // bw x bh patch of output pixels of one image; s2_* describe the output grid and the input's padded height

@@ -210,8 +210,8 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     } else if (e->autotune && !transposed && p[15] <= 0) {
                         // measure the modelled top candidates on the device once per (op, batch); every candidate accumulates in the
                         // same K order, so the choice never changes results
-                        int cBN[12], cMT[12], cPair[12];
-                        int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 6, cBN, cMT);
+                        int cBN[16], cMT[16], cPair[16];
+                        int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 12, cBN, cMT);
                         for (int k = 0; k < nc; ++k) cPair[k] = (e->mc_mode == 1 || e->mc_mode == 2) ? e->mc_mode : 0;
                         if (e->mc_mode == 3) {
                             const int np = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 4, cBN + nc, cMT + nc, 1);
@@ -238,7 +238,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                             if (!rc) cudaEventElapsedTime(&ms, ev0, ev1);
                             static const bool at_log = getenv("ADAS_B200_AT_LOG") != nullptr;
                             if (at_log) fprintf(stderr, "[autotune] op %zu M=%d N=%d K=%d taps=%d BN=%d mt=%d pair=%d : %.1f us\n", oi, g.M, g.N, Kc * ntaps, ntaps,
-                                                gc.BN, gc.mt_hint == 1 ? 1 : (gc.BN <= 128 ? 2 : 1), gc.mc_hint, rc ? -1.0 : ms * 1000.0 / 3.0);
+                                                gc.BN, gc.mt_hint, gc.mc_hint, rc ? -1.0 : ms * 1000.0 / 3.0);
                             if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_tc_v2_free(opaque); opaque = cand; }
                             else gemm_tc_v2_free(cand);
                         }

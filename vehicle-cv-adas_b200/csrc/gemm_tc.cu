@@ -381,7 +381,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 struct GemmV2 {
     GemmParams p;
-    int MT;          // 1 or 2 sub-tiles of 128 rows per CTA tile
+    int MT;          // 1..4 sub-tiles of 128 rows per CTA tile (they share every weight tile)
+    int sub_cols;    // TMEM columns per sub-tile accumulator
+    int acc_stages;  // 2 when two whole accumulator sets fit in the 512 TMEM columns (epilogue overlaps the next tile), else 1
     int slab;        // 1: ntaps == 9 handled as 3 dy-steps x 3 dx-taps from a shared slab
     int a_sub_bytes; // bytes of one A sub-tile in a stage
     int b_bytes;     // bytes of one B tile (BN rows), 1024-aligned
@@ -417,7 +419,9 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int taps_per_step = g.slab ? 3 : 1;
     const int ksteps = (g.slab ? 3 : p.ntaps) * p.kpt;
     const int BMT = BM * g.MT;
-    const int mt_cols = g.MT == 2 ? 128 : 0;      // TMEM column offset of sub-tile 1
+    const int mt_cols = g.sub_cols;               // TMEM column offset between sub-tiles
+    const int acc_stride = g.MT * g.sub_cols;     // TMEM columns per accumulator stage
+    const bool acc2 = g.acc_stages == 2;
     // work distribution: item w -> (n tile, m tile).  With multicast pairs both CTAs of a cluster walk the same items and
     // take the even / odd M tile of the pair, so they need the same weight tiles at the same time.
     const int cl2 = (g_mc | g_pair);
@@ -548,10 +552,10 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool skip_mma = (p.dbg & 2) != 0, no_wait = (p.dbg & 32) != 0;
             uint32_t it = 0, tile_it = 0;
             for (int w = w_first; w < g.work_items; w += w_step, ++tile_it) {
-                const int as = tile_it & 1;
-                mbar_wait(smem_u32(&tempty_bar[as]), ((tile_it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
+                const int as = acc2 ? (int)(tile_it & 1) : 0;
+                mbar_wait(smem_u32(&tempty_bar[as]), ((acc2 ? (tile_it >> 1) : tile_it) & 1u) ^ 1u);     // epilogue drained this accumulator stage
                 tcgen05_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)(as * 256);
+                const uint32_t d_base = tmem_base + (uint32_t)(as * acc_stride);
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
@@ -599,16 +603,17 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int et = threadIdx.x - 64;
         uint32_t tile_it = 0;
         for (int w = w_first; w < g.work_items; w += w_step, ++tile_it) {
-            const int as = tile_it & 1;
+            const int as = acc2 ? (int)(tile_it & 1) : 0;
+            const int bs = (int)(tile_it & 1);        // bias staging buffer (alternates even with one accumulator stage)
             TILE_OF(w, n_t, m_t)
             const int n0 = n_t * p.BN;
             const int m0 = m_t * BMT;
             if (!p.transposed) {
                 for (int j = et; j < p.BN; j += V2_THREADS - 64)
-                    s_bias[as][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+                    s_bias[bs][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            mbar_wait(smem_u32(&tfull_bar[as]), (tile_it >> 1) & 1u);
+            mbar_wait(smem_u32(&tfull_bar[as]), (acc2 ? (tile_it >> 1) : tile_it) & 1u);
             tcgen05_fence_after();
             for (int mt = 0; mt < g.MT; ++mt) {
                 int row = m0 + mt * BM + q * 32 + lane;
@@ -634,7 +639,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 float row_bias = 0.f;
                 if (p.transposed && p.bias != nullptr && row < p.M) row_bias = p.bias[row];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + mt * mt_cols);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_stride + mt * mt_cols);
                 const size_t res_ld = (size_t)(p.res_ld < 0 ? -p.res_ld : p.res_ld);
                 for (int c = half * 32; c < p.BN; c += 64) {
                     if (p.dbg & 16) break;
@@ -658,10 +663,10 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (row_ok && ncols > 0) {
                             float f[32];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v0[j]) + s_bias[as][c + j];
+                            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v0[j]) + s_bias[bs][c + j];
                             if (two) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) f[16 + j] = __uint_as_float(v1[j]) + s_bias[as][c + 16 + j];
+                                for (int j = 0; j < 16; ++j) f[16 + j] = __uint_as_float(v1[j]) + s_bias[bs][c + 16 + j];
                             }
                             if (has_res && p.res_ld < 0) {
 #pragma unroll
@@ -745,8 +750,14 @@ static int g_num_sms = 0;
 
 int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
     g->p = p;
-    g->MT = (p.BN <= 128) ? 2 : 1;
-    if (p.mt_hint == 1 || p.s2) g->MT = 1;
+    g->sub_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    g->MT = p.mt_hint >= 1 ? p.mt_hint : ((p.BN <= 128) ? 2 : 1);
+    static int force_mt = -1;
+    if (force_mt < 0) { const char* f = getenv("ADAS_B200_MT"); force_mt = f ? atoi(f) : 0; }
+    if (force_mt >= 1 && force_mt <= 4 && force_mt * g->sub_cols <= 512) g->MT = force_mt;     // test hook: exercise every sub-tile count
+    if (p.s2) g->MT = 1;
+    if (g->MT > 4 || g->MT * g->sub_cols > 512) return 1;
+    g->acc_stages = (2 * g->MT * g->sub_cols <= 512) ? 2 : 1;
     const int want_pair = (p.mc_hint == 2 && !p.s2 && p.BN % 32 == 0) ? 1 : 0;
     const int b_bytes = ((((want_pair ? p.BN / 2 : p.BN)) * BK * 2) + 1023) & ~1023;
     g->b_bytes = b_bytes;
@@ -852,23 +863,24 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out, int pair) {
     // (the multicast on/off variants of each returned candidate are tried by the autotuner in engine.cu)
     const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
-    struct C { double t; int BN, mt; } list[24];
+    struct C { double t; int BN, mt; } list[48];
     int n = 0;
     const int kpt = (Kc + 63) / 64;
     for (int ci = 0; ci < 10; ++ci) {
         int BN = cand[ci];
         if (BN > N) { if (ci + 1 < 10 && cand[ci + 1] >= N) continue; BN = (N + 15) / 16 * 16; }
         if (BN > 256) continue;
+        if (BN < 64 && N >= 64 && max_out > 1) continue;       // narrow tiles only ever win on narrow layers
         const int n_tiles = (N + BN - 1) / BN;
         if ((double)n_tiles * BN > 1.35 * N) continue;          // too much padded-N work
         bool dup = false;
         for (int k = 0; k < n; ++k) dup = dup || (list[k].BN == BN);
         if (dup) continue;
-        for (int mt = 1; mt <= 2; ++mt) {
-            if (mt == 2 && BN > 128) continue;
+        for (int mt = 1; mt <= 4; ++mt) {
+            if (mt >= 2 && BN > 128) continue;
             GemmParams p;
             memset(&p, 0, sizeof(p));
-            p.M = M; p.N = N; p.Kc = Kc; p.ntaps = ntaps; p.kpt = kpt; p.BN = BN; p.mt_hint = mt == 1 ? 1 : 0;
+            p.M = M; p.N = N; p.Kc = Kc; p.ntaps = ntaps; p.kpt = kpt; p.BN = BN; p.mt_hint = mt;
             p.mc_hint = pair ? 2 : 0;
             if (pair && BN % 32 != 0) continue;
             GemmV2 g;
@@ -878,17 +890,17 @@ int gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_
             const double bytes = ksteps * (g.MT * (g.slab ? SLAB_BYTES : A_STAGE_BYTES) + (g.slab ? 3 : 1) * (pair ? BN / 2 : BN) * 128.0);
             const double mma = (double)g.MT * ntaps * kpt * 2.0 * BN;
             const double epi = (double)g.MT * 128.0 * BN * 0.55;
-            const double per_tile = fmax(fmax(bytes / 32.0, mma), epi) + 600.0;
+            const double per_tile = (g.acc_stages == 2 ? fmax(fmax(bytes / 32.0, mma), epi) : fmax(bytes / 32.0, mma) + epi) + 600.0;
             const double waves = ceil((pair ? 2.0 * g.work_items : tiles) / 148.0);
             const double t = waves * per_tile + epi * 0.5 + 2500.0;
-            if (n < 24) { list[n].t = t; list[n].BN = BN; list[n].mt = mt; ++n; }
+            if (n < 48) { list[n].t = t; list[n].BN = BN; list[n].mt = mt; ++n; }
         }
     }
     // insertion sort by modelled time
     for (int i = 1; i < n; ++i) { C c = list[i]; int j = i - 1; while (j >= 0 && list[j].t > c.t) { list[j + 1] = list[j]; --j; } list[j + 1] = c; }
     if (n == 0) { list[0].BN = N <= 256 ? (N + 15) / 16 * 16 : 256; list[0].mt = list[0].BN <= 128 ? 2 : 1; n = 1; }
     if (n > max_out) n = max_out;
-    for (int i = 0; i < n; ++i) { BN_out[i] = list[i].BN; mt_hint_out[i] = list[i].mt == 1 ? 1 : 0; }
+    for (int i = 0; i < n; ++i) { BN_out[i] = list[i].BN; mt_hint_out[i] = list[i].mt; }
     return n;
 }
 

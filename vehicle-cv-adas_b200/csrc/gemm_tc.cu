@@ -396,6 +396,24 @@ struct GemmV2 {
     int work_items;  // scheduler items: tiles, or tile pairs when mc
 };
 
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// SiLU of four values with ONE reciprocal: 1/(1+t_i) = (prod_{j != i} (1+t_j)) / prod_j (1+t_j).  The SFU (16 lanes / clk / SM)
+// bounds the epilogue math, so 5 SFU ops per 4 elements instead of 8.  The exponent argument is clamped at -20 (SiLU(-20) = -4e-8,
+// below half precision) so the product of four (1 + e^20) stays inside fp32; the error is a few fp32 ulps.
+__device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
+    const float L = -1.4426950408889634f;
+    const float a0 = 1.0f + ex2_approx(fmaxf(x0, -20.f) * L);
+    const float a1 = 1.0f + ex2_approx(fmaxf(x1, -20.f) * L);
+    const float a2 = 1.0f + ex2_approx(fmaxf(x2, -20.f) * L);
+    const float a3 = 1.0f + ex2_approx(fmaxf(x3, -20.f) * L);
+    const float p01 = a0 * a1, p23 = a2 * a3;
+    const float r = rcp_approx(p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;
+    x0 *= r01 * a1; x1 *= r01 * a0; x2 *= r23 * a3; x3 *= r23 * a2;
+}
+
 // kCluster = false: plain launch, no cluster / cta_group::2 instructions in the binary (a kernel that contains them must be
 // launched with a cluster attribute).  kCluster = true: CTA pairs (TMA multicast or cta_group::2 MMA).
 template <bool kCluster>
@@ -601,6 +619,8 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp_idx & 3;
         const int half = (warp_idx - 2) >> 2;
         const int et = threadIdx.x - 64;
+        // 32-byte stores need 32-byte aligned rows
+        const bool wide_st = !(p.dbg & 512) && !p.out_f32 && (p.out_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
         uint32_t tile_it = 0;
         for (int w = w_first; w < g.work_items; w += w_step, ++tile_it) {
             const int as = acc2 ? (int)(tile_it & 1) : 0;
@@ -680,7 +700,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const int act = (p.dbg & 8) ? 0 : p.act;
                             if (act == 1) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+                                for (int j = 0; j < 32; j += 4) silu4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                             } else if (act == 2) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -702,6 +722,19 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     if (k * 4 < ncols) *reinterpret_cast<float4*>(op + k * 4) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
                             } else {
                                 __half* op = reinterpret_cast<__half*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
+                                if (wide_st && ncols == 32) {
+                                    // two 32-byte stores: every lane writes whole sectors of its row
+                                    uint32_t o[16];
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                                        o[j] = *reinterpret_cast<const uint32_t*>(&h);
+                                    }
+                                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                                                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + 16), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]),
+                                                 "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]) : "memory");
+                                } else
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     if (k * 8 < ncols) {
@@ -748,7 +781,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 static int g_num_sms = 0;
 
-int gemm_tc_v2_config(const GemmParams& p, GemmV2* g) {
+int gemm_tc_v2_config(const GemmParams& p_in, GemmV2* g) {
+    GemmParams p = p_in;
+    static int force_bn = -1;
+    if (force_bn < 0) { const char* f = getenv("ADAS_B200_BN"); force_bn = f ? atoi(f) : 0; }
+    if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && force_bn <= ((p.N + 15) / 16) * 16 && !p.transposed) p.BN = force_bn;   // test hook
     g->p = p;
     g->sub_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
     g->MT = p.mt_hint >= 1 ? p.mt_hint : ((p.BN <= 128) ? 2 : 1);
@@ -921,7 +958,7 @@ int gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner
     if (gemm_tc_v2_config(p, &L->g)) { delete L; ADAS_CHECK(false, "gemm_tc_v2: tile does not fit in shared memory (BN %d)", p.BN); }
     const uint32_t a_box_rows = L->g.slab ? SLAB_ROWS : BM;
     if (make_tmap_2d(&L->tmA, a_base, a_inner, a_rows, a_stride_bytes, 64, a_box_rows) ||
-        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)((L->g.mc | L->g.pair) ? p.BN / 2 : p.BN))) {
+        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)((L->g.mc | L->g.pair) ? L->g.p.BN / 2 : L->g.p.BN))) {
         delete L;
         return 1;
     }
@@ -935,7 +972,7 @@ int gemm_tc_v2_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C,
     GemmV2Launch* L = new GemmV2Launch();
     if (gemm_tc_v2_config(p, &L->g)) { delete L; ADAS_CHECK(false, "gemm_tc_v2_s2: tile does not fit in shared memory"); }
     if (make_tmap_4d_s2(&L->tmA, a_base, a_C, a_Wp, a_Hp, a_B, a_ld, 2u * (uint32_t)p.s2_bw, 2u * (uint32_t)p.s2_bh) ||
-        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)p.BN)) {
+        make_tmap_2d(&L->tmB, b_base, b_inner, b_rows, b_stride_bytes, 64, (uint32_t)L->g.p.BN)) {
         delete L;
         return 1;
     }

@@ -137,7 +137,8 @@ def run_b200(args):
     if rank != 0:
         plans = build_plans()
     from adas_b200.pipeline import AdasPipeline
-    pipe = AdasPipeline(plans["yolov8"][0], plans["ufldv2"][0], device=local, batch=B, box_score=BOX_SCORE, box_nms_iou=NMS_IOU, max_det=MAX_DET)
+    pipe = AdasPipeline(plans["yolov8"][0], plans["ufldv2"][0], device=local, batch=B, box_score=BOX_SCORE, box_nms_iou=NMS_IOU, max_det=MAX_DET,
+                        sets=args.sets, depth=args.depth)
 
     # one stream per rank; frames differ per step (pool larger than L2: 24 batches x 22 MB = 530 MB >> 126 MB)
     pool_batches = max(6, min(24, 192 // B))
@@ -389,6 +390,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=2, help="engine pairs the pipeline alternates between (batches in flight on the device)")
+    ap.add_argument("--depth", type=int, default=3, help="batches queued ahead of the tracker")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample (0 disables)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of the --impl reference arm")
     args = ap.parse_args()

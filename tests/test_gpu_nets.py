@@ -221,3 +221,43 @@ def test_detect_pair_concurrent_streams_equal_separate_calls():
     assert int(y_ref[4].sum()) > 0
     ye.close()
     ue.close()
+
+
+def test_pipeline_overlapped_equals_synchronous():
+    """AdasPipeline.step_pipelined (two engine pairs in flight, tracker one batch behind) returns, batch for batch, exactly what the
+    synchronous step() does: detections, lane points and track ids."""
+    from adas_b200.pipeline import AdasPipeline
+    ypath, _, _ = cached_plan("yolov8", scale="l")
+    upath, _, _ = cached_plan("ufldv2", backbone="18")
+    batches = [np.stack([synth.frame(40 + 2 * i + j) for j in range(2)]) for i in range(5)]
+
+    def run(pipelined: bool):
+        pipe = AdasPipeline(ypath, upath, device=0, batch=2, sets=2 if pipelined else 1, depth=3)
+        out = []
+        if pipelined:
+            for fr in batches:
+                r = pipe.step_pipelined(fr)
+                if r is not None:
+                    out.append(r)
+            out += pipe.flush()
+        else:
+            out = [pipe.step(fr) for fr in batches]
+        pipe.close()
+        return out
+
+    a, b = run(False), run(True)
+    assert len(a) == len(b) == len(batches)
+    dets = 0
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra.counts, rb.counts)
+        for i, n in enumerate(ra.counts):
+            dets += int(n)
+            assert np.array_equal(ra.boxes[i, :n], rb.boxes[i, :n]) and np.array_equal(ra.scores[i, :n], rb.scores[i, :n])
+            assert np.array_equal(ra.class_ids[i, :n], rb.class_ids[i, :n])
+        assert np.array_equal(ra.lane_npts, rb.lane_npts) and np.array_equal(ra.lane_status, rb.lane_status)
+        for i in range(ra.lane_pts.shape[0]):
+            for l in range(4):
+                assert np.array_equal(ra.lane_pts[i, l, :ra.lane_npts[i, l]], rb.lane_pts[i, l, :rb.lane_npts[i, l]])
+        key = lambda t: (t["track_id"], t["location"], t["score"], t["class_id"], t["curr_frame_number"], t["is_activated"], t["count"])
+        assert [[key(t) for t in fr] for fr in ra.tracks] == [[key(t) for t in fr] for fr in rb.tracks]
+    assert dets > 0

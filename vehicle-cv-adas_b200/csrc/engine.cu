@@ -967,7 +967,7 @@ int adas_associate(int device, int T, int D, const double* a_tlbr, const double*
     AssocScratch& s = g_as;
     const size_t nb = (size_t)(T > D ? T : D), nc = (size_t)T * D;
     if (s.device != device || nb > s.cap_boxes || nc > s.cap_cost) {
-        if (s.st == nullptr || s.device != device) { ADAS_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)); }
+        if (s.st == nullptr || s.device != device) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); ADAS_CUDA(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi)); }
         cudaFree(s.d_a); cudaFree(s.d_b); cudaFree(s.d_s); cudaFree(s.d_c); cudaFree(s.d_x); cudaFree(s.d_y);
         s.cap_boxes = nb < 256 ? 256 : nb * 2; s.cap_cost = nc < 65536 ? 65536 : nc * 2;
         ADAS_CUDA(cudaMalloc(&s.d_a, s.cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&s.d_b, s.cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&s.d_s, s.cap_boxes * 8));

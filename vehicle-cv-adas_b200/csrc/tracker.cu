@@ -138,7 +138,11 @@ namespace adas {
 
 static int ensure_scratch(adas_tracker* t, size_t nb, size_t nc) {
     if (t->st == nullptr) {
-        ADAS_CUDA(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+        // the association kernels are tiny and on the host's critical path: highest priority, so they are scheduled as soon as any
+        // CTA slot frees up between the detectors' persistent conv kernels
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ADAS_CUDA(cudaStreamCreateWithPriority(&t->st, cudaStreamNonBlocking, prio_hi));
         const size_t wc = (size_t)lap_max_cols() + 1;
         ADAS_CUDA(cudaMalloc(&t->d_th, 8)); ADAS_CUDA(cudaMalloc(&t->d_v, wc * 8)); ADAS_CUDA(cudaMalloc(&t->d_mv, wc * 8));
         ADAS_CUDA(cudaMalloc(&t->d_wi, wc * 12)); ADAS_CUDA(cudaMalloc(&t->d_meta, 32)); ADAS_CUDA(cudaMalloc(&t->d_co, 16));

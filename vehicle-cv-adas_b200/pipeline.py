@@ -6,13 +6,14 @@ stream:  a worker thread makes ONE library call (`adas_detect_pair`) that enqueu
 on their own CUDA streams before waiting for either -- the tail waves of one network's persistent conv kernels are
 back-filled by the other's (measured 3.96 vs 4.35 ms per 8-frame step; driving the two streams from two Python threads
 instead was slower, the interpreter lock serialises the launches) -- while the host thread runs the ByteTrack updates of
-the PREVIOUS batch:
+the PREVIOUS batch; consecutive batches alternate between two engine pairs so the device never waits for the host:
 the tracker is sequential in time per stream, so it pipelines one batch behind the detectors.  Per-frame
 results are identical to calling the three detectors frame by frame.
 """
 from __future__ import annotations
 
 import sys
+import threading
 from collections import deque
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
@@ -34,29 +35,40 @@ class StepResult:
 
 class AdasPipeline:
     def __init__(self, yolo_plan: str, ufld_plan: str, device: int = 0, batch: int = 8, box_score: float = 0.4, box_nms_iou: float = 0.45,
-                 max_det: int = 300, class_names: Optional[List[str]] = None, depth: int = 2):
+                 max_det: int = 300, class_names: Optional[List[str]] = None, depth: int = 3, sets: int = 2):
         self.batch, self.box_score, self.box_nms_iou, self.max_det = batch, box_score, box_nms_iou, max_det
-        self.yolo = _capi.Engine(yolo_plan, device, max_batch=batch)
-        self.ufld = _capi.Engine(ufld_plan, device, max_batch=batch)
+        # `sets` independent (object engine, lane engine) pairs: consecutive batches alternate between them so the next batch's
+        # kernels are already queued on the device (own streams, own activation buffers) while the previous batch drains --
+        # no idle gap between library calls, and four streams' worth of kernels to back-fill partial waves.
+        self.sets = []
+        for _ in range(max(1, sets)):
+            self.sets.append((_capi.Engine(yolo_plan, device, max_batch=batch), _capi.Engine(ufld_plan, device, max_batch=batch), threading.Lock()))
+        self.yolo, self.ufld = self.sets[0][0], self.sets[0][1]
+        self._next_set = 0
         self.tracker = BYTETracker(names=class_names or [], device=device)
         self.tracker.reset()
         self.class_names = class_names
-        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._pool = ThreadPoolExecutor(max_workers=len(self.sets))
         sys.setswitchinterval(2e-4)       # the detector thread only needs the interpreter between two library calls
         self.depth = max(1, depth)                     # batches in flight in the detector thread
         self._queue = deque()
 
     def close(self):
         self._pool.shutdown(wait=True)
-        self.yolo.close()
-        self.ufld.close()
+        for y, u, _ in self.sets:
+            y.close()
+            u.close()
 
     # -- stages -------------------------------------------------------------------------------------------
-    def _detect_both(self, frames, on_device: bool, shape):
-        return _capi.detect_pair(self.yolo, self.ufld, frames, self.box_score, self.box_nms_iou, self.max_det, on_device, shape)
+    def _detect_both(self, frames, on_device: bool, shape, k: int = 0):
+        y, u, lock = self.sets[k]
+        with lock:                        # one batch at a time per engine pair
+            return _capi.detect_pair(y, u, frames, self.box_score, self.box_nms_iou, self.max_det, on_device, shape)
 
     def _detect(self, frames, on_device: bool, shape):
-        return self._pool.submit(self._detect_both, frames, on_device, shape)
+        k = self._next_set
+        self._next_set = (k + 1) % len(self.sets)
+        return self._pool.submit(self._detect_both, frames, on_device, shape, k)
 
     def _track(self, r: StepResult) -> None:
         import time

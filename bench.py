@@ -219,6 +219,16 @@ def run_b200(args):
             ms = float(t.item())
         return ms, launches, clocks
 
+    if args.profile_steps:
+        # profiler target (ncu --profile-from-start off): warm up (autotune, graph capture), then expose N steps; no numbers printed
+        run_steps(Wm + 2, 0, True)
+        barrier()
+        torch.cuda.profiler.start()
+        run_steps(args.profile_steps, Wm, True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        pipe.close()
+        return
     ms_dev, launches, clocks = timed(True)
     ms_e2e, _, clocks_e2e = timed(False)
 
@@ -271,6 +281,18 @@ def run_b200(args):
         }
         if cpu is not None:
             result["cpu_baseline"] = cpu
+        if world == 1 and args.other_configs:
+            # BASELINE configs[1] / configs[2]: the two conv stacks alone at batch 32 (GEMM launches of one pass, timed like `roofline`)
+            pipe.close()
+            other = {}
+            for name, key, gf in (("yolov8l_b32 (configs[1])", "yolov8", GFLOP_YOLOV8L), ("ufldv2_res34_b32 (configs[2])", "ufldv2", GFLOP_UFLD34)):
+                eng = _capi.Engine(plans[key][0], local, max_batch=32)
+                ms_g, n_g = eng.time_ops(32, 1 << 1, 3)
+                ms_a, _ = eng.time_ops(32, 0xFFFFFFFF, 3)
+                eng.close()
+                other[name] = {"gemm_tflops": round(gf * 32 / ms_g, 1), "frac_of_peak": round(gf * 32 / ms_g / peak, 4), "gemm_ms": round(ms_g, 3),
+                               "all_plan_kernels_ms": round(ms_a, 3), "images_per_s_plan_only": round(32e3 / ms_a, 1), "gemm_launches": n_g}
+            result["other_configs"] = other
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
@@ -390,6 +412,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile-steps", type=int, default=0, help="profiler target: run N steps between cudaProfilerStart/Stop and exit")
+    ap.add_argument("--other-configs", type=int, default=1, help="also time the two conv stacks alone at batch 32 (N=1 only)")
     ap.add_argument("--sets", type=int, default=2, help="engine pairs the pipeline alternates between (batches in flight on the device)")
     ap.add_argument("--depth", type=int, default=3, help="batches queued ahead of the tracker")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample (0 disables)")

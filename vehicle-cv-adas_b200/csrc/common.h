@@ -76,6 +76,7 @@ int  gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inne
 int  gemm_tc_v2_run(void* opaque, cudaStream_t st);
 void gemm_tc_v2_free(void* opaque);
 void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out);
+int  gemm_tc_v2_grid(const void* opaque);
 int  gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out, int pair = 0);
 int  gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st);
 int  gemm_simt_launch(const GemmParams& p, cudaStream_t st);

@@ -986,6 +986,11 @@ int gemm_tc_v2_run(void* opaque, cudaStream_t st) {
 }
 
 void gemm_tc_v2_free(void* opaque) { delete static_cast<GemmV2Launch*>(opaque); }
+int gemm_tc_v2_grid(const void* opaque) {
+    const GemmV2& g = static_cast<const GemmV2Launch*>(opaque)->g;
+    const int n = (g.mc | g.pair) ? 2 * g.work_items : g.total_tiles;
+    return n < 148 ? n : 148;
+}
 
 int gemm_tc_smem_bytes(int BN, int stages) {
     const int b_stage = ((BN * BK * 2) + 1023) & ~1023;

@@ -74,8 +74,10 @@ def build_plans(seed: int = 0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  One nvidia-smi process
+    logs every 10 ms for the whole run (its start-up takes longer than a short timed region); each line carries nvidia-smi's own
+    timestamp and `window(t0, t1)` keeps the samples taken between the two wall-clock marks of a timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
@@ -83,35 +85,52 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 3.0
+            while not self.lines and time.time() < t_end:      # first sample = the logger is up
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    @staticmethod
+    def _stamp(txt: str, arrival: float) -> float:
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return arrival
+
+    def window(self, t0: float, t1: float):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)                                        # let the samples of the last few ms arrive
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for arrival, ln in list(self.lines):
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
+                continue
+            ts = self._stamp(f[0], arrival)
+            if ts < t0 - 0.002 or ts > t1 + 0.002:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[2])); mx.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -194,12 +213,13 @@ def run_b200(args):
         for r in pipe.flush():
             gather(r)
 
+    sampler = ClockSampler(local)
+
     def timed(on_device: bool):
         run_steps(Wm, 0, on_device)
         barrier()
         n0 = _capi.launch_count()
-        sampler = ClockSampler(local)
-        sampler.start()
+        w0 = time.time()
         pipe.yolo.event_record(0)
         t0 = time.perf_counter()
         run_steps(K, Wm, on_device)
@@ -208,7 +228,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         ms_dev = max(pipe.yolo.elapsed_ms(0, pipe.ufld, 1), pipe.yolo.elapsed_ms(0, pipe.yolo, 1))
         ms_wall = (time.perf_counter() - t0) * 1e3
-        clocks = sampler.stop()
+        clocks = sampler.window(w0, time.time())
         launches = _capi.launch_count() - n0
         barrier()
         # the tracker of the last batch runs on the host after the last device event: take the larger of the two clocks
@@ -229,8 +249,10 @@ def run_b200(args):
         torch.cuda.profiler.stop()
         pipe.close()
         return
+    sampler.start()
     ms_dev, launches, clocks = timed(True)
     ms_e2e, _, clocks_e2e = timed(False)
+    sampler.close()
 
     result = None
     if rank == 0:

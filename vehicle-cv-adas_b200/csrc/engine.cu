@@ -241,7 +241,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                                                 gc.BN, gc.mt_hint, gc.mc_hint, rc ? -1.0 : ms * 1000.0 / 3.0);
                             // score: isolated latency, optionally weighted towards SM-time (CTAs x duration) because other streams'
                             // kernels back-fill the SMs a small grid leaves free
-                            static const float at_alpha = getenv("ADAS_B200_AT_ALPHA") ? (float)atof(getenv("ADAS_B200_AT_ALPHA")) : 0.3f;
+                            static const float at_alpha = getenv("ADAS_B200_AT_ALPHA") ? (float)atof(getenv("ADAS_B200_AT_ALPHA")) : 0.f;
                             if (!rc) ms *= (1.f - at_alpha) + at_alpha * (float)gemm_tc_v2_grid(cand) / 148.f;
                             if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_tc_v2_free(opaque); opaque = cand; }
                             else gemm_tc_v2_free(cand);

@@ -3,7 +3,9 @@
 Mirrors /root/reference coreEngine.py: `EngineBase` (7-39: path check, `framework_type` property, the three
 abstract methods) and the concrete-engine surface of TensorRTEngine (120-157) / OnnxEngine (159-186):
 `providers`, `engine_dtype`, `get_engine_input_shape()`, `get_engine_output_shape()`, `engine_inference(x)`.
-`B200Engine` accepts a `.b200w` plan (written by `adas_b200.plan`) instead of `.onnx` / `.trt`.
+`B200Engine` accepts a `.b200w` plan (written by `adas_b200.plan`) or the reference's own `.onnx` model file, which is
+converted once to a cached plan by `adas_b200.onnx_import` (the counterpart of convertOnnxToTensorRT.py); `.trt` engines are
+TensorRT-private binaries and are not readable.
 """
 import abc
 import os
@@ -14,14 +16,14 @@ from . import _capi
 
 
 class EngineBase(abc.ABC):
-    """Currently supports the B200 plan framework (the reference supports Onnx/TensorRT)."""
+    """Supports B200 plans and ONNX model files (the reference supports Onnx/TensorRT, coreEngine.py:12-14)."""
 
-    SUFFIXES = (".b200w",)
+    SUFFIXES = (".b200w", ".onnx")
 
     def __init__(self, model_path):
         if not os.path.isfile(model_path):
             raise Exception("The model path [%s] can't not found!" % model_path)
-        assert model_path.endswith(self.SUFFIXES), "B200 Parameters must be a .b200w file."
+        assert model_path.endswith(self.SUFFIXES), "B200 Parameters must be a .b200w or .onnx file."
         self._framework_type = None
 
     @property
@@ -62,6 +64,10 @@ class B200Engine(EngineBase):
         EngineBase.__init__(self, plan_path)
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
+        if plan_path.endswith(".onnx"):
+            from .onnx_import import plan_from_onnx
+            plan_path = plan_from_onnx(plan_path)        # parsed and packed once, cached next to the temp dir (ADAS_B200_PLAN_CACHE)
+        self.plan_path = plan_path
         self.handle = _capi.Engine(plan_path, device=device, max_batch=max_batch, conv_impl=conv_impl)
         self.providers = "B200ExecutionProvider(sm_100a)"
         self.framework_type = "b200"

@@ -155,3 +155,25 @@ def test_wrong_architecture_is_reported(tmp_path):
     m = onnx_import.read_onnx(path)
     with pytest.raises(Exception, match="expected a|no parameters left|expected"):
         plan.build_yolov5(onnx_import.OnnxWeights(m), "s")
+
+
+def test_checkpoint_conversion_matches_seeded_plan(tmp_path):
+    """convert.py on a reference-style checkpoint ({'model': state_dict} with DataParallel 'module.' prefixes,
+    convertPytorchToONNX.py:77-84) and on an ONNX file, through the command-line entry point."""
+    from adas_b200 import convert
+    W = plan.synth_weights("yolov5", 7)
+    ref = plan.build_yolov5(W, "n")
+    ckpt = str(tmp_path / "v5n.pth")
+    torch.save({"model": {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in W.state_dict.items()}}, ckpt)
+    sd = convert.load_checkpoint_state_dict(ckpt)
+    assert set(sd) == set(W.state_dict)
+    got = convert.plan_from_state_dict(sd, "yolov5", scale="n")
+    assert ref.ops == got.ops and all(np.array_equal(a, b) for a, b in zip(ref.tensors, got.tensors))     # same fold -> identical bytes
+    assert convert.main([ckpt, "--kind", "yolov5", "--scale", "n"]) == 0
+    assert open(str(tmp_path / "v5n.b200w"), "rb").read(8) == b"B200PLAN"
+    with pytest.raises(Exception, match="--kind is required"):
+        convert.convert(ckpt)
+    onnx_path = str(tmp_path / "v5n_fused.onnx")
+    _export(_fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), onnx_path)
+    out = convert.convert(onnx_path)
+    assert out.endswith("v5n_fused.b200w") and os.path.getsize(out) > 1_000_000

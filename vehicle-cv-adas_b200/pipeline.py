@@ -44,6 +44,13 @@ class AdasPipeline:
         for _ in range(max(1, sets)):
             self.sets.append((_capi.Engine(yolo_plan, device, max_batch=batch), _capi.Engine(ufld_plan, device, max_batch=batch), threading.Lock()))
         self.yolo, self.ufld = self.sets[0][0], self.sets[0][1]
+        # build every launch program here, one engine at a time: the per-layer tile autotune times candidates on the device and
+        # must not run while another engine is busy (with two pairs the first two batches would otherwise tune concurrently);
+        # the second pass captures the CUDA graphs.
+        for y, u, _ in self.sets:
+            for e in (y, u):
+                e.run(batch)
+                e.run(batch)
         self._next_set = 0
         self.tracker = BYTETracker(names=class_names or [], device=device)
         self.tracker.reset()

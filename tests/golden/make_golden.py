@@ -179,9 +179,37 @@ def gen_ufld_net_pin():
     json.dump(out, open(os.path.join(OUT, "ufld_net_pin.json"), "w"), indent=1)
 
 
+def gen_birdview():
+    """perspectiveTransformation.py: matrices after each update type, bird-view points, curvature / offset."""
+    from TrafficLaneDetector.ufldDetector.perspectiveTransformation import PerspectiveTransformation
+    out = {}
+    for case, (seed, kind) in enumerate([(s, k) for s in range(8) for k in ("Default", "Top", "Bottom", None)]):
+        left, right = synth.ego_lanes(100 + seed)
+        t = PerspectiveTransformation((1280, 720))
+        if kind is not None:
+            t.updateTransformParams(left, right, kind)
+        bl, br = t.transformToBirdViewPoints(left), t.transformToBirdViewPoints(right)
+        img = np.zeros((720, 1280, 3), np.uint8)
+        (direction, curv), off = t.calcCurveAndOffset(img, bl, br)
+        out[f"c{case}_src"], out[f"c{case}_M"], out[f"c{case}_Minv"] = t.src, t.M, t.M_inv
+        out[f"c{case}_bl"], out[f"c{case}_br"] = np.asarray(bl), np.asarray(br)
+        out[f"c{case}_curve"] = np.array([{"L": -1.0, "F": 0.0, "R": 1.0}[direction], curv, off])
+        out[f"c{case}_draw_sha"] = np.frombuffer(bytes.fromhex(sha(img)), np.uint8)
+        warped = t.transformToBirdView(synth.frame(seed))
+        out[f"c{case}_warp_sha"] = np.frombuffer(bytes.fromhex(sha(warped)), np.uint8)
+    t = PerspectiveTransformation((1280, 720))
+    assert t.transformToBirdViewPoints([]) == [] and t.calcCurveAndOffset(np.zeros((720, 1280, 3), np.uint8), [], []) == ((None, None), None)
+    np.savez_compressed(os.path.join(OUT, "birdview.npz"), **out)
+    print("birdview.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "birdview":
+        gen_birdview()
+        sys.exit(0)
     gen_nms()
     gen_yolo()
     gen_ufld()
     gen_track()
     gen_ufld_net_pin()
+    gen_birdview()

@@ -120,3 +120,19 @@ def track_sequence(seed: int, frames: int = 40, objects: int = 8):
             labels.append("class5")
         seq.append((boxes, scores, labels))
     return seq
+
+
+def ego_lanes(seed: int, img_w: int = 1280, img_h: int = 720):
+    """Two plausible ego-lane polylines in the frontal view: lists of (int x, int y) converging towards the horizon, with a mild
+    seeded curvature (inputs of the bird-view geometry tests)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(18, 40))
+    ys = np.linspace(img_h * rng.uniform(0.55, 0.7), img_h - 1, n)
+    t = (ys - ys[0]) / (ys[-1] - ys[0])
+    bend = rng.uniform(-120, 120)
+    centre = img_w * rng.uniform(0.42, 0.58) + bend * (1 - t) ** 2
+    half = img_w * (0.04 + rng.uniform(0.16, 0.24) * t)
+    jit = rng.normal(0, 1.5, (2, n))
+    left = [(int(x), int(y)) for x, y in zip(centre - half + jit[0], ys)]
+    right = [(int(x), int(y)) for x, y in zip(centre + half + jit[1], ys)]
+    return left, right

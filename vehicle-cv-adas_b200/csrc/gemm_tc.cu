@@ -416,8 +416,11 @@ __device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3
 
 // kCluster = false: plain launch, no cluster / cta_group::2 instructions in the binary (a kernel that contains them must be
 // launched with a cluster attribute).  kCluster = true: CTA pairs (TMA multicast or cta_group::2 MMA).
-template <bool kCluster>
-__global__ void __launch_bounds__(V2_THREADS, 1)
+// kEpiWarps = 8 (product) or 16 (EXPERIMENTAL, ADAS_B200_EPI16=1): four epilogue warps per scheduler instead of two, 16-column
+// batches so that the register budget of a 576-thread CTA (112 / thread) holds.  ncu on the 8-warp kernel: the epilogue issues
+// ~370 instructions per 32-column batch but takes ~3x the issue time -- latency-bound with two warps per scheduler.
+template <bool kCluster, int kEpiWarps = 8>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmV2 g) {
     const int g_pair = kCluster ? g.pair : 0;
     const int g_mc = kCluster ? g.mc : 0;
@@ -457,7 +460,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), ((V2_THREADS - 64) / 32) * (g_pair ? 2 : 1));   // one arrive per epilogue warp; pair: both CTAs' epilogues drain the leader's MMA
+            mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps * (g_pair ? 2 : 1));   // one arrive per epilogue warp; pair: both CTAs' epilogues drain the leader's MMA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -629,10 +632,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int n0 = n_t * p.BN;
             const int m0 = m_t * BMT;
             if (!p.transposed) {
-                for (int j = et; j < p.BN; j += V2_THREADS - 64)
+                for (int j = et; j < p.BN; j += 32 * kEpiWarps)
                     s_bias[bs][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if constexpr (kEpiWarps == 16) asm volatile("bar.sync 1, 512;" ::: "memory");
+            else asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(smem_u32(&tfull_bar[as]), (acc2 ? (tile_it >> 1) : tile_it) & 1u);
             tcgen05_fence_after();
             for (int mt = 0; mt < g.MT; ++mt) {
@@ -661,6 +665,96 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (p.transposed && p.bias != nullptr && row < p.M) row_bias = p.bias[row];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_stride + mt * mt_cols);
                 const size_t res_ld = (size_t)(p.res_ld < 0 ? -p.res_ld : p.res_ld);
+                if constexpr (kEpiWarps == 16) {
+                    // four warps per TMEM lane quarter take interleaved 16-column batches
+                    const int part = (warp_idx - 2) >> 2;
+                    for (int c = part * 16; c < p.BN; c += 64) {
+                        if (p.dbg & 16) break;
+                        uint32_t v[16];
+                        tmem_ld16(taddr + (uint32_t)c, v);
+                        const int n = n0 + c;
+                        const int ncols = min(16, p.N - n);
+                        uint4 rr[2];
+                        const bool has_res = (p.res != nullptr) && row_ok && !p.transposed;
+                        if (has_res) {
+                            const __half* rp = p.res + (size_t)row * res_ld + n;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if (k * 8 < ncols) rr[k] = *reinterpret_cast<const uint4*>(rp + k * 8);
+                        }
+                        tmem_ld_wait();
+                        if (!p.transposed) {
+                            if (row_ok && ncols > 0) {
+                                float f[16];
+                                const float4* sb4 = reinterpret_cast<const float4*>(&s_bias[bs][c]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 b4 = sb4[j];
+                                    f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                                }
+                                if (has_res && p.res_ld < 0) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k)
+                                        if (k * 8 < ncols) {
+                                            const __half2* h = reinterpret_cast<const __half2*>(&rr[k]);
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) { float2 tt = __half22float2(h[j]); f[k * 8 + 2 * j] += tt.x; f[k * 8 + 2 * j + 1] += tt.y; }
+                                        }
+                                }
+                                const int act = (p.dbg & 8) ? 0 : p.act;
+                                if (act == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 16; j += 4) silu4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                                } else if (act == 2) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                                }
+                                if (has_res && p.res_ld > 0) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k)
+                                        if (k * 8 < ncols) {
+                                            const __half2* h = reinterpret_cast<const __half2*>(&rr[k]);
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) { float2 tt = __half22float2(h[j]); f[k * 8 + 2 * j] += tt.x; f[k * 8 + 2 * j + 1] += tt.y; }
+                                        }
+                                }
+                                if ((p.dbg & 4) && f[0] != 123456.f) continue;
+                                if (p.out_f32) {
+                                    float* op = reinterpret_cast<float*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (k * 4 < ncols) *reinterpret_cast<float4*>(op + k * 4) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                                } else {
+                                    __half* op = reinterpret_cast<__half*>(p.out) + (size_t)row * (size_t)p.out_ld + n;
+                                    uint32_t o[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                                        o[j] = *reinterpret_cast<const uint32_t*>(&h);
+                                    }
+                                    if (wide_st && ncols == 16) {
+                                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                                                     "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                                    } else {
+                                        *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+                                        if (ncols > 8) *reinterpret_cast<uint4*>(op + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                                    }
+                                }
+                            }
+                        } else if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int col = n + j;
+                                if (col < p.N) {
+                                    const float x = act_apply(__uint_as_float(v[j]) + row_bias, p.act);
+                                    if (p.out_f32) reinterpret_cast<float*>(p.out)[(size_t)col * (size_t)p.out_ld + row] = x;
+                                    else reinterpret_cast<__half*>(p.out)[(size_t)col * (size_t)p.out_ld + row] = __float2half_rn(x);
+                                }
+                            }
+                        }
+                    }
+                } else
                 for (int c = half * 32; c < p.BN; c += 64) {
                     if (p.dbg & 16) break;
                     const bool two = (c + 16) < p.BN;          // BN is a multiple of 16: a batch is 32 or 16 columns
@@ -846,6 +940,12 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         attr = true;
     }
     const int smem = g.p.stages * g.stage_bytes + 1024;
+    static int epi16 = -1;
+    if (epi16 < 0) {
+        const char* ev = getenv("ADAS_B200_EPI16");
+        epi16 = (ev && ev[0] == '1') ? 1 : 0;
+        if (epi16) ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    }
     static int pdl = -1;
     if (pdl < 0) { const char* pe = getenv("ADAS_B200_PDL"); pdl = (pe && pe[0] == '0') ? 0 : 1; }
     if (pdl && !(g.mc | g.pair)) {
@@ -853,7 +953,7 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         gp.pdl = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(g.total_tiles < g_num_sms ? g.total_tiles : g_num_sms, 1, 1);
-        cfg.blockDim = dim3(V2_THREADS, 1, 1);
+        cfg.blockDim = dim3(epi16 ? 64 + 32 * 16 : V2_THREADS, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr1;
@@ -861,7 +961,8 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         attr1.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = &attr1;
         cfg.numAttrs = 1;
-        ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false>, tmA, tmB, gp));
+        if (epi16) ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false, 16>, tmA, tmB, gp));
+        else ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false>, tmA, tmB, gp));
         count_launch();
         return 0;
     }

@@ -686,13 +686,8 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (!p.transposed) {
                             if (row_ok && ncols > 0) {
                                 float f[16];
-                                const float4* sb4 = reinterpret_cast<const float4*>(&s_bias[bs][c]);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 b4 = sb4[j];
-                                    f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                                }
+                                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[bs][c + j];
                                 if (has_res && p.res_ld < 0) {
 #pragma unroll
                                     for (int k = 0; k < 2; ++k)

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+import re
 import struct
 import tempfile
 from dataclasses import dataclass, field
@@ -349,11 +350,21 @@ def recognise(model: OnnxModel) -> ModelSpec:
     if cout0 not in _V8_WIDTH:
         raise Exception(f"unrecognised YOLO width: first convolution has {cout0} output channels")
     scale = _V8_WIDTH[cout0]
+    named_nc = None                     # the class count is read from the head's own tensors when their names survived
+    for name, cw, _ in w.convs:
+        if re.fullmatch(r"model\.\d+\.cv3\.\d+\.2\.weight", name):      # YOLOv8 Detect.cv3[i][2]: Conv2d(c3, nc, 1)
+            named_nc = cw.shape[0]
+        elif re.fullmatch(r"model\.\d+\.m\.\d+\.weight", name) and cw.shape[2:] == (1, 1) and cw.shape[0] % 3 == 0:
+            named_nc = cw.shape[0] // 3 - 5                                     # YOLOv5 Detect.m[i]: Conv2d(c, 3 * (nc + 5), 1)
     if k0 == 6:                                                               # yolov5 v6.x stem Conv(3, c, 6, 2, 2)
+        if named_nc is not None:
+            return ModelSpec("yolov5", scale, named_nc, in_h or 640, in_w or 640)
         no = [s[0] for s in shapes if s[2:] == (1, 1)][-1]                    # Detect.m[i]: 3 * (nc + 5)
         assert no % 3 == 0, f"YOLOv5 head with {no} outputs"
         return ModelSpec("yolov5", scale, no // 3 - 5, in_h or 640, in_w or 640)
     if k0 == 3:
+        if named_nc is not None:
+            return ModelSpec("yolov8", scale, named_nc, in_h or 640, in_w or 640)
         # Detect.cv3[i][2]: Conv2d(c3, nc, 1) -- the last 1x1 convolutions before the (optional) fixed DFL conv
         ones = [s for s in shapes if s[2:] == (1, 1) and s[0] != 1]
         return ModelSpec("yolov8", scale, ones[-1][0], in_h or 640, in_w or 640)

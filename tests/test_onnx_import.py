@@ -177,3 +177,25 @@ def test_checkpoint_conversion_matches_seeded_plan(tmp_path):
     _export(_fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), onnx_path)
     out = convert.convert(onnx_path)
     assert out.endswith("v5n_fused.b200w") and os.path.getsize(out) > 1_000_000
+
+
+def test_engine_accepts_onnx_path_and_fails_loudly_without_a_device(tmp_path, monkeypatch):
+    """`B200Engine("model.onnx")` converts and caches the plan, then hands it to the C ABI; with no sm_100 device here the library
+    must raise (there is no CPU fallback on the product path)."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from adas_b200.coreEngine import B200Engine
+    W = plan.synth_weights("yolov5", 8)
+    plan.build_yolov5(W, "n")
+    path = str(tmp_path / "v5n.onnx")
+    _export(_fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), path)
+    monkeypatch.setenv("ADAS_B200_PLAN_CACHE", str(tmp_path / "cache"))
+    with pytest.raises(Exception) as ei:
+        B200Engine(path, device=0)
+    assert "onnx" not in str(ei.value).lower() or "cuda" in str(ei.value).lower()       # the failure is the device, not the conversion
+    cached = os.listdir(str(tmp_path / "cache"))
+    assert len(cached) == 1 and cached[0].startswith("v5n-") and cached[0].endswith(".b200w")
+    with pytest.raises(Exception, match="can't not found"):
+        B200Engine(str(tmp_path / "missing.onnx"))
+    with pytest.raises(AssertionError):
+        B200Engine(__file__)                           # wrong suffix: same assertion style as coreEngine.py:12-14

@@ -17,7 +17,7 @@ fits); it stays on the host like SURVEY row K, the heavy parts (`warpPerspective
 in the reference.  The numeric core is separated from the drawing so that it can be tested against golden vectors produced by the
 reference class (tests/golden/make_golden.py -> birdview.npz).
 """
-from typing import List, Optional, Tuple, Union
+from typing import Optional, Tuple, Union
 
 import cv2
 import numpy as np

@@ -635,6 +635,40 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = et; j < p.BN; j += 32 * kEpiWarps)
                     s_bias[bs][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             }
+            // (16-warp variant) the output row of every sub-tile and its halo mask need two integer divisions: computed here, while
+            // the main loop is still running, instead of after the accumulator is ready (ncu source page of the 8-warp kernel:
+            // this block holds ~40 % as many stall samples as a whole 32-column batch)
+            int pre_row[4] = {0, 0, 0, 0};
+            bool pre_ok[4] = {false, false, false, false};
+            if constexpr (kEpiWarps == 16) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    if (mt < g.MT) {
+                        int row = m0 + mt * BM + q * 32 + lane;
+                        bool row_ok = row < p.M;
+                        if (p.s2) {
+                            const int r = q * 32 + lane;
+                            const int per_img = p.s2_tw * p.s2_th;
+                            const int b = m_t / per_img;
+                            const int rem = m_t - b * per_img;
+                            const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
+                            const int j = r / p.s2_bw, i = r - j * p.s2_bw;
+                            const int yo = ty * p.s2_bh + j, xo = tx * p.s2_bw + i;
+                            row_ok = (r < p.s2_bw * p.s2_bh) && (yo < p.s2_Ho) && (xo < p.s2_Wo);
+                            row = (b * (p.s2_Ho + 2) + yo + 1) * (p.s2_Wo + 2) + xo + 1;
+                        } else if (p.mask_H > 0 && row_ok) {
+                            const int Wp = p.mask_W + 2;
+                            const int img = (p.mask_H + 2) * Wp;
+                            const int pp = row % img;
+                            const int yy = pp / Wp;
+                            const int xx = pp - yy * Wp;
+                            row_ok = (yy >= 1) && (yy <= p.mask_H) && (xx >= 1) && (xx <= p.mask_W);
+                        }
+                        pre_row[mt] = row;
+                        pre_ok[mt] = row_ok;
+                    }
+                }
+            }
             if constexpr (kEpiWarps == 16) asm volatile("bar.sync 1, 512;" ::: "memory");
             else asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(smem_u32(&tfull_bar[as]), (acc2 ? (tile_it >> 1) : tile_it) & 1u);
@@ -642,6 +676,10 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int mt = 0; mt < g.MT; ++mt) {
                 int row = m0 + mt * BM + q * 32 + lane;
                 bool row_ok = row < p.M;
+                if constexpr (kEpiWarps == 16) {
+                    row = mt == 0 ? pre_row[0] : mt == 1 ? pre_row[1] : mt == 2 ? pre_row[2] : pre_row[3];
+                    row_ok = mt == 0 ? pre_ok[0] : mt == 1 ? pre_ok[1] : mt == 2 ? pre_ok[2] : pre_ok[3];
+                } else
                 if (p.s2) {
                     const int r = q * 32 + lane;
                     const int mt_idx = m_t;

@@ -199,3 +199,23 @@ def test_engine_accepts_onnx_path_and_fails_loudly_without_a_device(tmp_path, mo
         B200Engine(str(tmp_path / "missing.onnx"))
     with pytest.raises(AssertionError):
         B200Engine(__file__)                           # wrong suffix: same assertion style as coreEngine.py:12-14
+
+
+def test_truncated_or_foreign_files_are_rejected_cleanly(tmp_path):
+    W = plan.synth_weights("yolov5", 9)
+    plan.build_yolov5(W, "n")
+    path = str(tmp_path / "v5n.onnx")
+    _export(_fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), path)
+    blob = open(path, "rb").read()
+    rng = np.random.default_rng(0)
+    for k, cut in enumerate([10, 1000, len(blob) // 3, len(blob) - 7]):
+        p = tmp_path / f"cut{k}.onnx"
+        p.write_bytes(blob[:cut])
+        with pytest.raises(Exception):
+            onnx_import.build_plan(onnx_import.read_onnx(str(p)))
+    junk = tmp_path / "junk.onnx"
+    junk.write_bytes(rng.integers(0, 256, 4096, dtype=np.uint8).tobytes())
+    with pytest.raises(Exception):
+        onnx_import.build_plan(onnx_import.read_onnx(str(junk)))
+    with pytest.raises(Exception, match="can't not found"):
+        onnx_import.read_onnx(str(tmp_path / "nope.onnx"))

@@ -215,8 +215,17 @@ class OnnxModel:
 
 def read_onnx(path: str) -> OnnxModel:
     """ModelProto: producer_name=2, graph=7, opset_import=8;  GraphProto: node=1, initializer=5, input=11, output=12."""
+    if not os.path.isfile(path):
+        raise Exception("The model path [%s] can't not found!" % path)
     with open(path, "rb") as f:
         data = memoryview(f.read())
+    try:
+        return _read_model(data, path)
+    except (IndexError, ValueError, struct.error, UnicodeDecodeError) as e:
+        raise Exception("The model path [%s] is not a readable ONNX file (%s: %s)" % (path, type(e).__name__, e)) from e
+
+
+def _read_model(data: memoryview, path: str) -> OnnxModel:
     graph, opset, producer = None, 0, ""
     for fno, wt, v in _fields(data):
         if fno == 7:

@@ -419,7 +419,8 @@ __device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3
 // kEpiWarps = 8 (product) or 16 (EXPERIMENTAL, ADAS_B200_EPI16=1): four epilogue warps per scheduler instead of two, 16-column
 // batches so that the register budget of a 576-thread CTA (112 / thread) holds.  ncu on the 8-warp kernel: the epilogue issues
 // ~370 instructions per 32-column batch but takes ~3x the issue time -- latency-bound with two warps per scheduler.
-template <bool kCluster, int kEpiWarps = 8>
+// kHoist (EXPERIMENTAL, ADAS_B200_HOIST=1 with the 8-warp epilogue): output rows / halo masks computed before the accumulator wait.
+template <bool kCluster, int kEpiWarps = 8, bool kHoist = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmV2 g) {
     const int g_pair = kCluster ? g.pair : 0;
@@ -640,7 +641,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // this block holds ~40 % as many stall samples as a whole 32-column batch)
             int pre_row[4] = {0, 0, 0, 0};
             bool pre_ok[4] = {false, false, false, false};
-            if constexpr (kEpiWarps == 16) {
+            if constexpr (kEpiWarps == 16 || kHoist) {
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) {
                     if (mt < g.MT) {
@@ -676,7 +677,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int mt = 0; mt < g.MT; ++mt) {
                 int row = m0 + mt * BM + q * 32 + lane;
                 bool row_ok = row < p.M;
-                if constexpr (kEpiWarps == 16) {
+                if constexpr (kEpiWarps == 16 || kHoist) {
                     row = mt == 0 ? pre_row[0] : mt == 1 ? pre_row[1] : mt == 2 ? pre_row[2] : pre_row[3];
                     row_ok = mt == 0 ? pre_ok[0] : mt == 1 ? pre_ok[1] : mt == 2 ? pre_ok[2] : pre_ok[3];
                 } else
@@ -973,11 +974,14 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         attr = true;
     }
     const int smem = g.p.stages * g.stage_bytes + 1024;
-    static int epi16 = -1;
+    static int epi16 = -1, hoist = 0;
     if (epi16 < 0) {
         const char* ev = getenv("ADAS_B200_EPI16");
         epi16 = (ev && ev[0] == '1') ? 1 : 0;
         if (epi16) ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        const char* hv = getenv("ADAS_B200_HOIST");
+        hoist = (!epi16 && hv && hv[0] == '1') ? 1 : 0;
+        if (hoist) ADAS_CUDA(cudaFuncSetAttribute(gemm_tc_v2_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     }
     static int pdl = -1;
     if (pdl < 0) { const char* pe = getenv("ADAS_B200_PDL"); pdl = (pe && pe[0] == '0') ? 0 : 1; }
@@ -995,6 +999,7 @@ int gemm_tc_v2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
         cfg.attrs = &attr1;
         cfg.numAttrs = 1;
         if (epi16) ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false, 16>, tmA, tmB, gp));
+        else if (hoist) ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false, 8, true>, tmA, tmB, gp));
         else ADAS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_v2_kernel<false>, tmA, tmB, gp));
         count_launch();
         return 0;

@@ -432,6 +432,7 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_holder;
     __shared__ float s_bias[2][256];
+    __shared__ __align__(16) float s_bias_al[2][256];     // 16-warp variant only (vector loads); unused -> dropped elsewhere
 
     const GemmParams& p = g.p;
     const int warp_idx = threadIdx.x >> 5;
@@ -633,8 +634,11 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int n0 = n_t * p.BN;
             const int m0 = m_t * BMT;
             if (!p.transposed) {
-                for (int j = et; j < p.BN; j += 32 * kEpiWarps)
-                    s_bias[bs][j] = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+                for (int j = et; j < p.BN; j += 32 * kEpiWarps) {
+                    const float bv = (p.bias != nullptr && (n0 + j) < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+                    if constexpr (kEpiWarps == 16) s_bias_al[bs][j] = bv;
+                    else s_bias[bs][j] = bv;
+                }
             }
             // (16-warp variant) the output row of every sub-tile and its halo mask need two integer divisions: computed here, while
             // the main loop is still running, instead of after the accumulator is ready (ncu source page of the 8-warp kernel:
@@ -725,8 +729,13 @@ gemm_tc_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (!p.transposed) {
                             if (row_ok && ncols > 0) {
                                 float f[16];
+                                const float4* sb4 = reinterpret_cast<const float4*>(&s_bias_al[bs][c]);      // c is a multiple of 16
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[bs][c + j];
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 b4 = sb4[j];
+                                    f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                                }
                                 if (has_res && p.res_ld < 0) {
 #pragma unroll
                                     for (int k = 0; k < 2; ++k)

@@ -202,6 +202,11 @@ int adas_engine_run(adas_engine* e, int batch);   /* replay the plan on whatever
 int adas_engine_event_record(adas_engine* e, int slot);
 int adas_event_elapsed_ms(adas_engine* ea, int slot_a, adas_engine* eb, int slot_b, float* ms);
 int adas_engine_time_ops(adas_engine* e, int batch, unsigned type_mask, int iters, float* ms_per_iter, int* launches);
+/* per-layer table: adas_engine_num_steps = launches of one plan replay at `batch`; adas_engine_time_step replays launch
+ * `step` alone, `iters` times back to back between two events (operands L2-warm), and returns its plan op type and a
+ * description of the GEMM shape / tile choice (empty for non-GEMM steps). */
+int adas_engine_num_steps(adas_engine* e, int batch, int* n);
+int adas_engine_time_step(adas_engine* e, int batch, int step, int iters, float* ms_per_iter, int* op_type, char* desc, int desc_cap);
 
 /* ---- optional multi-GPU gather -------------------------------------------------------------
  * (no reference counterpart: the reference is single-GPU)  The gather of

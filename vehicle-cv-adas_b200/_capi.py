@@ -23,7 +23,7 @@ SYMBOLS = [
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
-    "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_detect_pair",
+    "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
     "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_get", "adas_tracker_count",
 ]
 
@@ -176,6 +176,18 @@ class Engine:
         ms, n = C.c_float(), C.c_int()
         check(lib().adas_engine_time_ops(self._h, batch, C.c_uint(type_mask), iters, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def num_steps(self, batch: int) -> int:
+        n = C.c_int()
+        check(lib().adas_engine_num_steps(self._h, batch, C.byref(n)))
+        return int(n.value)
+
+    def time_step(self, batch: int, step: int, iters: int):
+        """(ms per launch, plan op type, description) of one launch of the plan replayed alone."""
+        ms, t = C.c_float(), C.c_int()
+        buf = C.create_string_buffer(256)
+        check(lib().adas_engine_time_step(self._h, batch, step, iters, C.byref(ms), C.byref(t), buf, 256))
+        return float(ms.value), int(t.value), buf.value.decode()
 
     # engine_inference: fp32 NCHW host -> list of fp32 host arrays
     def infer(self, x: np.ndarray):

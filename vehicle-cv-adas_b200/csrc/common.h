@@ -77,6 +77,7 @@ int  gemm_tc_v2_run(void* opaque, cudaStream_t st);
 void gemm_tc_v2_free(void* opaque);
 void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out);
 int  gemm_tc_v2_grid(const void* opaque);
+void gemm_tc_v2_describe(const void* opaque, char* out, int cap);
 int  gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out, int pair = 0);
 int  gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st);
 int  gemm_simt_launch(const GemmParams& p, cudaStream_t st);

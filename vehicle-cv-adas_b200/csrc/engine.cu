@@ -42,6 +42,7 @@ struct DevBuf {
 struct Program {   // launch list for one batch size
     std::vector<std::function<int(cudaStream_t)>> steps;
     std::vector<uint32_t> step_type;
+    std::vector<std::string> step_desc;   // human-readable shape / tile choice per step (adas_engine_step_desc)
     cudaGraphExec_t graph = nullptr;
     int runs = 0;
 };
@@ -253,6 +254,12 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                         if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
                     }
                     std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
+                    {
+                        char d[256];
+                        gemm_tc_v2_describe(opaque, d, sizeof(d));
+                        prog->step_desc.resize(prog->step_type.size());
+                        prog->step_desc.back() = d;
+                    }
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
                 } else if (e->conv_impl == 0) {
                     ADAS_CHECK(!s2, "op %zu: the v1 kernel has no stride-2 mode (unset ADAS_B200_GEMM)", oi);
@@ -920,6 +927,48 @@ int adas_event_elapsed_ms(adas_engine* ea, int slot_a, adas_engine* eb, int slot
     ADAS_CUDA(cudaEventElapsedTime(ms, ea->events[slot_a], eb->events[slot_b]));
     return 0;
 }
+int adas_engine_time_step(adas_engine* e, int batch, int step, int iters, float* ms_per_iter, int* op_type, char* desc, int desc_cap) {
+    ADAS_CHECK(e != nullptr && batch >= 1 && batch <= e->max_batch && iters >= 1, "bad arguments");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    auto it = e->programs.find(batch);
+    if (it == e->programs.end()) {
+        Program prog;
+        if (build_program(e, batch, &prog)) return 1;
+        it = e->programs.emplace(batch, std::move(prog)).first;
+    }
+    Program& pg = it->second;
+    ADAS_CHECK(step >= 0 && step < (int)pg.steps.size(), "step %d outside [0, %d)", step, (int)pg.steps.size());
+    cudaEvent_t a, b;
+    ADAS_CUDA(cudaEventCreate(&a)); ADAS_CUDA(cudaEventCreate(&b));
+    if (pg.steps[step](e->stream)) return 1;
+    ADAS_CUDA(cudaEventRecord(a, e->stream));
+    for (int r = 0; r < iters; ++r) if (pg.steps[step](e->stream)) return 1;
+    ADAS_CUDA(cudaEventRecord(b, e->stream));
+    ADAS_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    ADAS_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_per_iter = ms / iters;
+    if (op_type) *op_type = (int)pg.step_type[step];
+    if (desc && desc_cap > 0) {
+        const char* d = step < (int)pg.step_desc.size() ? pg.step_desc[step].c_str() : "";
+        snprintf(desc, (size_t)desc_cap, "%s", d);
+    }
+    return 0;
+}
+int adas_engine_num_steps(adas_engine* e, int batch, int* n) {
+    ADAS_CHECK(e != nullptr && batch >= 1 && batch <= e->max_batch, "bad arguments");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    auto it = e->programs.find(batch);
+    if (it == e->programs.end()) {
+        Program prog;
+        if (build_program(e, batch, &prog)) return 1;
+        it = e->programs.emplace(batch, std::move(prog)).first;
+    }
+    *n = (int)it->second.steps.size();
+    return 0;
+}
+
 int adas_engine_time_ops(adas_engine* e, int batch, unsigned type_mask, int iters, float* ms_per_iter, int* launches) {
     ADAS_CHECK(e != nullptr && batch >= 1 && batch <= e->max_batch && iters >= 1, "bad arguments");
     ADAS_CUDA(cudaSetDevice(e->device));

@@ -1140,6 +1140,13 @@ int gemm_tc_v2_grid(const void* opaque) {
     return n < 148 ? n : 148;
 }
 
+void gemm_tc_v2_describe(const void* opaque, char* out, int cap) {
+    const GemmV2& g = static_cast<const GemmV2Launch*>(opaque)->g;
+    snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d pair=%d", g.p.M, g.p.N,
+             g.p.Kc * g.p.ntaps, g.p.ntaps, g.p.act, g.p.res ? (g.p.res_ld < 0 ? -1 : 1) : 0, g.p.out_f32, g.p.s2, g.p.transposed, g.p.BN, g.MT, g.slab,
+             g.p.stages, g.acc_stages, g.total_tiles, g.pair | (g.mc << 1));
+}
+
 int gemm_tc_smem_bytes(int BN, int stages) {
     const int b_stage = ((BN * BK * 2) + 1023) & ~1023;
     return stages * (A_STAGE_BYTES + b_stage) + 1024;

@@ -112,6 +112,7 @@ __global__ void lap_kernel(const double* __restrict__ cost, const int64_t* __res
                 if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
             }
             if (bj == 0x7fffffff) break;      // no finite candidate (NaN costs): leave the row unmatched instead of spinning
+            __syncwarp();                     // the scan above wrote minv[j] / way[j] with a different lane -> column mapping than the update below
             const double delta = bd;
             const int j1 = bj;
             for (int j = lane; j <= m; j += 32) {

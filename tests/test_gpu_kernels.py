@@ -15,7 +15,10 @@ from gpu_util import from_padded, halo_is_zero, to_padded
 pytestmark = pytest.mark.gpu
 
 
-def _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual=None, out_f32=False, pad=None, seed=0, im_c=None):
+def _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual=None, out_f32=False, pad=None, seed=0, im_c=None, tile=None,
+              out_slice=None):
+    """tile = (BN, MT) forces the tile shape of the tcgen05 kernel; out_slice = (C_total, coff) writes the result into a channel
+    slice of a wider (concat) buffer whose other channels must stay untouched."""
     if pad is None and k == 1:
         pad = 0
     rng = np.random.default_rng(seed)
@@ -28,7 +31,11 @@ def _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual=None, out_
     Ho, Wo = (H + 2 * pd - k) // s + 1, (W + 2 * pd - k) // s + 1
     if residual:
         res_view = pb.new_padded(Ho, Wo, cout)
-    out = pb.conv(xin, w, b, k, s, act, res=res_view, res_pre_act=(residual == "pre"), out_f32=out_f32, pad=pad)
+    out_view = None
+    if out_slice:
+        cat = pb.new_padded(Ho, Wo, out_slice[0])
+        out_view = pb.sub(cat, out_slice[1], cout)
+    out = pb.conv(xin, w, b, k, s, act, res=res_view, res_pre_act=(residual == "pre"), out_f32=out_f32, pad=pad, out=out_view, tile=tile)
     path = str(tmp_path / f"conv_{impl}_{seed}.b200w")
     pb.write(path)
     eng = _capi.Engine(path, device=0, max_batch=B, conv_impl=impl)
@@ -38,10 +45,18 @@ def _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual=None, out_
     if residual:
         r = rng.standard_normal((B, cout, Ho, Wo)).astype(np.float32)
         eng.write_buffer(res_view.buf, to_padded(r, cout))
+    sentinel = None
+    if out_slice:               # the rest of the concat buffer holds a sentinel pattern (interior only: halos stay zero)
+        sentinel = rng.standard_normal((B, out_slice[0], Ho, Wo)).astype(np.float32)
+        eng.write_buffer(out.buf, to_padded(sentinel, out_slice[0]))
     for _ in range(3):          # eager, graph capture, graph replay
         eng.run(B)
     got_buf = eng.read_buffer(out.buf, B)
-    got = from_padded(got_buf, B, Ho, Wo, 0, cout)
+    got = from_padded(got_buf, B, Ho, Wo, out.coff, cout)
+    if out_slice:
+        full = from_padded(got_buf, B, Ho, Wo, 0, out_slice[0])
+        keep = np.ones(out_slice[0], bool); keep[out.coff:out.coff + cout] = False
+        assert np.array_equal(full[:, keep], sentinel.astype(np.float16).astype(np.float32)[:, keep]), "conv wrote outside its channel slice"
     xt = torch.from_numpy(x).half().float()
     wt = torch.from_numpy(w).half().float()
     ref = F.conv2d(xt, wt, torch.from_numpy(b), stride=s, padding=pd)
@@ -83,6 +98,68 @@ def test_conv_parity(tmp_path, impl, case):
     err = _run_conv(tmp_path, impl, B, cin, cout, H, W, k, s, act, residual, f32, seed=cin + cout + k)
     tol = 2e-3 if f32 else 4e-3      # fp16 output rounding: 2^-11 relative
     assert err < tol, f"impl {impl} case {case}: relative error {err}"
+
+
+TILE_CASES = [
+    # (B cin cout H W k s act residual) , (BN, MT)   -- tcgen05 kernel only: every epilogue / accumulator / operand-fetch mode
+    ((2, 256, 256, 40, 40, 3, 1, 1, "post"), (256, 1)),     # plain 9 taps, staged stores, 4 chunks
+    ((2, 256, 256, 40, 40, 3, 1, 1, None), (256, 2)),       # one 512-column accumulator set
+    ((2, 256, 256, 40, 40, 3, 1, 1, "post"), (128, 2)),     # slab, two sub-tiles, two accumulator stages
+    ((2, 128, 128, 80, 80, 3, 1, 1, None), (128, 1)),       # slab, many tiles per CTA (accumulator / staging ping-pong)
+    ((2, 128, 128, 48, 80, 3, 1, 2, "pre"), (128, 4)),      # four sub-tiles, one accumulator stage, residual before ReLU
+    ((2, 256, 256, 20, 20, 3, 1, 1, None), (64, 3)),        # 64-wide tiles, three sub-tiles
+    ((1, 256, 320, 40, 40, 3, 1, 1, None), (128, 1)),       # N = 320: last N tile half outside the tensor (TMA clips it)
+    ((1, 256, 320, 40, 40, 3, 1, 1, None), (192, 1)),       # 192-wide tiles
+    ((1, 256, 320, 40, 40, 3, 1, 1, None), (160, 1)),       # direct-store epilogue (BN not a multiple of 64)
+    ((2, 256, 512, 40, 40, 3, 2, 1, None), (256, 1)),       # stride 2, 4-D TMA store of output patches
+    ((2, 256, 512, 40, 40, 3, 2, 1, None), (128, 2)),       # stride 2 with two patches per CTA tile
+    ((3, 128, 256, 80, 80, 3, 2, 1, None), (128, 3)),       # stride 2, three patches, patch count not a multiple of MT
+    ((1, 64, 64, 160, 96, 3, 2, 2, "pre"), (64, 2)),        # stride 2 with residual, 48-wide output rows (clipped patches)
+    ((2, 1024, 512, 40, 40, 1, 1, 1, None), (256, 2)),      # 1x1, long K, 256x256 tiles
+    ((2, 320, 128, 80, 80, 1, 1, 1, None), (128, 3)),       # 1x1, K = 320 (five k-blocks)
+    ((1, 192, 64, 17, 23, 1, 1, 1, None), (64, 1)),         # K tail, ragged M
+    ((2, 64, 80, 20, 20, 1, 1, 0, None), (80, 1)),          # fp16 N = 80 through the direct path
+]
+
+
+@pytest.mark.parametrize("case,tile", TILE_CASES)
+def test_conv_tile_shapes(tmp_path, case, tile):
+    B, cin, cout, H, W, k, s, act, residual = case
+    err = _run_conv(tmp_path, 0, B, cin, cout, H, W, k, s, act, residual, False, seed=cin + cout + k + tile[0] + tile[1], tile=tile)
+    assert err < 4e-3, f"case {case} tile {tile}: relative error {err}"
+
+
+def test_conv_tile_shapes_agree_bitwise(tmp_path):
+    """Every tile shape accumulates in the same K order: outputs are bit-identical whatever (BN, MT) is chosen."""
+    B, cin, cout, H, W = 2, 128, 256, 40, 40
+    outs = []
+    for i, tile in enumerate(((256, 1), (256, 2), (128, 1), (128, 2), (64, 4), (192, 1), (160, 1))):
+        rng = np.random.default_rng(5)
+        pb = plan.PlanBuilder(plan.MODEL_YOLOV5, 3, H, W)
+        xin = pb.new_padded(H, W, cin)
+        w = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float32)
+        b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+        out = pb.conv(xin, w, b, 3, 1, 1, tile=tile)
+        path = str(tmp_path / f"bit_{i}.b200w")
+        pb.write(path)
+        eng = _capi.Engine(path, device=0, max_batch=B)
+        eng.write_buffer(xin.buf, to_padded(rng.standard_normal((B, cin, H, W)).astype(np.float32), cin))
+        eng.run(B)
+        outs.append(eng.read_buffer(out.buf, B).copy())
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o.view(np.uint16), outs[0].view(np.uint16))
+
+
+def test_conv_into_concat_slice(tmp_path):
+    """Producers write their channel slice of a concat buffer; the neighbours' channels and the halo must stay untouched."""
+    for (case, tile, sl) in (((2, 128, 128, 40, 40, 3, 1, 1, "post"), (128, 2), (384, 128)),
+                             ((2, 256, 64, 20, 24, 1, 1, 1, None), (64, 1), (192, 64)),
+                             ((2, 128, 256, 40, 40, 3, 2, 1, None), (128, 2), (512, 256)),
+                             ((1, 64, 40, 24, 24, 1, 1, 1, None), None, (96, 56))):
+        B, cin, cout, H, W, k, s, act, residual = case
+        err = _run_conv(tmp_path, 0, B, cin, cout, H, W, k, s, act, residual, False, seed=cout + sl[0], tile=tile, out_slice=sl)
+        assert err < 4e-3, (case, tile, sl, err)
 
 
 @pytest.mark.parametrize("impl", [1, 0])

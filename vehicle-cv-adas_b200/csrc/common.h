@@ -85,6 +85,18 @@ int  gemm_tc_smem_bytes(int BN, int stages);
 int  gemm_tc_pick_stages(int BN, int num_kb);
 int  make_tmap_4d_s2(CUtensorMap* tm, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint64_t ld_elems,
                      uint32_t box_w_src, uint32_t box_h_src);
+int  make_tmap_4d(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t ld_elems, uint64_t Wp, uint64_t Hp,
+                  uint32_t box_c, uint32_t box_w, uint32_t box_h);
+// v3 kernel (gemm_v3.cu): the product path
+int  gemm_v3_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
+                     const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
+int  gemm_v3_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, uint64_t a_Wp, uint64_t a_Hp, uint64_t a_B, uint64_t a_ld,
+                        const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
+int  gemm_v3_run(void* opaque, cudaStream_t st);
+void gemm_v3_free(void* opaque);
+int  gemm_v3_grid(const void* opaque);
+void gemm_v3_describe(const void* opaque, char* out, int cap);
+int  gemm_v3_candidates(const GemmParams& base, int max_out, int* BN_out, int* mt_out);
 int  make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                   uint32_t box_inner, uint32_t box_rows);
 

@@ -57,6 +57,7 @@ struct adas_engine {
     int conv_impl = 0;
     bool use_graph = true;
     bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
+    int gemm_ver = 3;             // 3 = gemm_v3.cu (product); ADAS_B200_GEMM=v2 / v1 select the round-1 kernels (A/B baselines)
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
     int mc_mode = 0;              // ADAS_B200_MC: 0 single-CTA tiles, 1 TMA-multicast pairs (measured: no gain), 2 cta_group::2 MMA pairs,
                                   // 3 autotune per layer between single CTAs and cta_group::2 pairs
@@ -191,6 +192,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     g.A = wptr; g.a_ld = Ktot; g.Wt = aptr; g.w_ld = (int)ab.C;
                     g.out_ld = (int)ob.C;
                 }
+                if (p[17] > 0) g.mt_hint = p[17];       // plan-forced sub-tile count (test hook of plan.py)
                 g.Kc = Kc; g.ntaps = ntaps; g.Wp = (int)ab.W + 2; g.kpt = (Kc + 63) / 64; g.BN = BN;
                 g.stages = gemm_tc_pick_stages(BN, ntaps * g.kpt);
                 g.act = act; g.out_f32 = ob.dtype == 1 ? 1 : 0;
@@ -203,7 +205,57 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 }
                 g.out = static_cast<uint8_t*>(e->dbufs[out_buf].ptr) + (size_t)out_coff * elem_size(ob.dtype);
                 if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
-                if (e->conv_impl == 0 && !e->gemm_v1) {
+                if (e->conv_impl == 0 && e->gemm_ver == 3) {
+                    // ---- product path: gemm_v3.cu ----
+                    void* opaque = nullptr;
+                    auto prep = [&](const GemmParams& gc, void** out) -> int {
+                        if (s2) return gemm_v3_prepare_s2(gc, aptr, (uint64_t)Kc, (uint64_t)ab.W + 2, (uint64_t)ab.H + 2, (uint64_t)batch, (uint64_t)ab.C, opB,
+                                                          b_inner, b_rows_u, b_stride, out);
+                        return gemm_v3_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, out);
+                    };
+                    if (!transposed && p[15] <= 0) {
+                        // tile candidates ranked by the cost model; with autotuning the best few are timed on the device once per
+                        // (op, batch).  Every candidate accumulates in the same K order, so the choice never changes results.
+                        int cBN[16], cMT[16];
+                        const int nc = gemm_v3_candidates(g, e->autotune ? 10 : 1, cBN, cMT);
+                        float best_ms = 1e30f;
+                        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+                        if (nc > 1) { ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1)); }
+                        for (int ci = 0; ci < nc; ++ci) {
+                            GemmParams gc = g;
+                            gc.BN = cBN[ci]; gc.mt_hint = cMT[ci];
+                            void* cand = nullptr;
+                            if (prep(gc, &cand)) continue;
+                            if (nc == 1) { opaque = cand; break; }
+                            int rc = gemm_v3_run(cand, e->stream);
+                            if (!rc) {
+                                cudaEventRecord(ev0, e->stream);
+                                for (int r = 0; r < 4 && !rc; ++r) rc = gemm_v3_run(cand, e->stream);
+                                cudaEventRecord(ev1, e->stream);
+                                if (cudaEventSynchronize(ev1) != cudaSuccess) rc = 1;
+                            }
+                            float ms = 1e30f;
+                            if (!rc) cudaEventElapsedTime(&ms, ev0, ev1);
+                            static const bool at_log = getenv("ADAS_B200_AT_LOG") != nullptr;
+                            if (at_log) fprintf(stderr, "[autotune] op %zu M=%d N=%d K=%d taps=%d s2=%d BN=%d mt=%d : %.1f us\n", oi, g.M, g.N, Kc * ntaps, ntaps, s2,
+                                                gc.BN, gc.mt_hint, rc ? -1.0 : ms * 1000.0 / 4.0);
+                            if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_v3_free(opaque); opaque = cand; }
+                            else gemm_v3_free(cand);
+                        }
+                        if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+                        ADAS_CHECK(opaque != nullptr, "op %zu: no GEMM tile configuration could be launched (%s)", oi, g_err);
+                    } else {
+                        if (prep(g, &opaque)) return 1;
+                    }
+                    std::shared_ptr<void> keep(opaque, gemm_v3_free);
+                    {
+                        char d[256];
+                        gemm_v3_describe(opaque, d, sizeof(d));
+                        prog->step_desc.resize(prog->step_type.size());
+                        prog->step_desc.back() = d;
+                    }
+                    prog->steps.push_back([keep](cudaStream_t st) { return gemm_v3_run(keep.get(), st); });
+                } else if (e->conv_impl == 0 && !e->gemm_v1) {
                     void* opaque = nullptr;
                     if (s2) {
                         if (gemm_tc_v2_prepare_s2(g, aptr, (uint64_t)Kc, (uint64_t)ab.W + 2, (uint64_t)ab.H + 2, (uint64_t)batch, (uint64_t)ab.C,
@@ -468,6 +520,7 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->use_graph = !(ng && ng[0] == '1');
     const char* gv = getenv("ADAS_B200_GEMM");
     e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
+    e->gemm_ver = (gv && strcmp(gv, "v1") == 0) ? 1 : (gv && strcmp(gv, "v2") == 0) ? 2 : 3;
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
     const char* mcv = getenv("ADAS_B200_MC");

@@ -23,132 +23,9 @@
 
 namespace adas {
 
-static constexpr int BM = 128;
-static constexpr int BK = 64;                       // fp16 elements per k-block = 128 bytes = one swizzle row
-static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-static constexpr int NUM_THREADS = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint16_t mask) {
-    // multicast: the box lands at the same shared-memory offset (and signals the same barrier offset) in every CTA of `mask`
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-// ---- cta_group::2 (CTA pair) variants: one MMA spans both SMs of the pair (M = 256), each CTA stages its own 128 rows of
-// A and HALF of the weight tile; only the leader CTA (cluster rank 0) issues MMAs and commits.
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t leader_bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(leader_bar)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                         // layout: SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float act_apply(float x, int act) {
-    if (act == 1) return __fdividef(x, 1.0f + __expf(-x));   // SiLU
-    if (act == 2) return fmaxf(x, 0.0f);                     // ReLU
-    return x;
-}
+}  // namespace adas
+#include "tc_common.cuh"
+namespace adas {
 
 __global__ void __launch_bounds__(NUM_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -375,9 +252,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_off(uint32_t smem_addr) {
     d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;        // base offset: row phase inside the 8-row swizzle atom
     return d;
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 struct GemmV2 {
     GemmParams p;
@@ -396,23 +270,6 @@ struct GemmV2 {
     int work_items;  // scheduler items: tiles, or tile pairs when mc
 };
 
-
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// SiLU of four values with ONE reciprocal: 1/(1+t_i) = (prod_{j != i} (1+t_j)) / prod_j (1+t_j).  The SFU (16 lanes / clk / SM)
-// bounds the epilogue math, so 5 SFU ops per 4 elements instead of 8.  The exponent argument is clamped at -20 (SiLU(-20) = -4e-8,
-// below half precision) so the product of four (1 + e^20) stays inside fp32; the error is a few fp32 ulps.
-__device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
-    const float L = -1.4426950408889634f;
-    const float a0 = 1.0f + ex2_approx(fmaxf(x0, -20.f) * L);
-    const float a1 = 1.0f + ex2_approx(fmaxf(x1, -20.f) * L);
-    const float a2 = 1.0f + ex2_approx(fmaxf(x2, -20.f) * L);
-    const float a3 = 1.0f + ex2_approx(fmaxf(x3, -20.f) * L);
-    const float p01 = a0 * a1, p23 = a2 * a3;
-    const float r = rcp_approx(p01 * p23);
-    const float r01 = r * p23, r23 = r * p01;
-    x0 *= r01 * a1; x1 *= r01 * a0; x2 *= r23 * a3; x3 *= r23 * a2;
-}
 
 // kCluster = false: plain launch, no cluster / cta_group::2 instructions in the binary (a kernel that contains them must be
 // launched with a cluster attribute).  kCluster = true: CTA pairs (TMA multicast or cta_group::2 MMA).
@@ -1230,6 +1087,25 @@ int make_tmap_4d_s2(CUtensorMap* tm, const void* base, uint64_t C, uint64_t Wp, 
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ADAS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4-D, stride 2) failed: %d", (int)r);
+    return 0;
+}
+
+// plain 4-D tiled map over [C, W, H, B] (row pitch Wp pixels, image pitch Hp rows): used for TMA STORES of output patches into the
+// interior of a padded NHWC grid (the tensor extent is the interior, so the unit clips partial patches and never touches the halo)
+int make_tmap_4d(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t ld_elems, uint64_t Wp, uint64_t Hp,
+                 uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+    PFN_encodeTiled fn = get_encode_fn();
+    ADAS_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    ADAS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0, "TMA 4-D map alignment");
+    ADAS_CHECK(box_w <= 256 && box_h <= 256 && box_c * 2 <= 128, "TMA 4-D box too large (%u x %u x %u)", box_c, box_w, box_h);
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {ld_elems * 2, Wp * ld_elems * 2, Hp * Wp * ld_elems * 2};
+    cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ADAS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4-D) failed: %d (C=%llu W=%llu H=%llu B=%llu)", (int)r, (unsigned long long)C,
+               (unsigned long long)W, (unsigned long long)H, (unsigned long long)B);
     return 0;
 }
 

@@ -194,7 +194,8 @@ class PlanBuilder:
         self.ops.append((typ, p, f))
 
     def conv(self, x: View, w: np.ndarray, b: Optional[np.ndarray], k: int, s: int, act: int, out: Optional[View] = None,
-             res: Optional[View] = None, res_pre_act: bool = False, out_f32: bool = False, pad: Optional[int] = None) -> View:
+             res: Optional[View] = None, res_pre_act: bool = False, out_f32: bool = False, pad: Optional[int] = None,
+             tile: Optional[Tuple[int, int]] = None) -> View:
         """w: folded [Cout, Cin_real, k, k] fp32.  x.C may exceed Cin_real (zero-padded image channel)."""
         cout, cin_real = int(w.shape[0]), int(w.shape[1])
         pad = k // 2 if pad is None else pad
@@ -238,8 +239,9 @@ class PlanBuilder:
             if Kpad != wk.shape[1]:
                 wk = np.concatenate([wk, np.zeros((wk.shape[0], Kpad - wk.shape[1]), np.float32)], 1)
         w_t = self.tensor(wk.astype(np.float16))
+        bn, mt = tile if tile is not None else (0, 0)          # (BN, MT) forced by tests; 0 = cost model + autotune
         self._op(OP_GEMM, [a.buf, a.coff, Kc, ntaps, w_t, bias_t, n_store, act, res_buf, res_coff, 1 if res_pre_act else 0,
-                           out.buf, out.coff, 1, 0, 0, s2])
+                           out.buf, out.coff, 1, 0, bn, s2, mt])
         return View(out.buf, out.coff, cout, Ho, Wo)
 
     def stem7x7s2(self, x: View, w: np.ndarray, b: np.ndarray, act: int) -> View:

@@ -30,7 +30,11 @@ extern "C" {
 typedef struct adas_engine adas_engine;   /* opaque: one plan (network) on one device */
 
 /* model kinds stored in the plan header */
-enum { ADAS_MODEL_YOLOV8 = 0, ADAS_MODEL_YOLOV5 = 1, ADAS_MODEL_UFLDV2 = 2 };
+enum { ADAS_MODEL_YOLOV8 = 0, ADAS_MODEL_YOLOV5 = 1, ADAS_MODEL_UFLDV2 = 2,
+       /* adas_yolo_postprocess only: `raw` is the sigmoid-only head of a YOLOv5-lite export; YoloLiteParameters.lite_postprocess
+        * (ObjectDetector/yoloDetector.py:36-50, model_type == ObjectModelType.YOLOV5_LITE) runs on the device first.  A lite PLAN
+        * is a YOLOV5 plan whose header meta[2] != 0 (adas_engine_meta). */
+       ADAS_MODEL_YOLOV5_LITE = 3 };
 
 /* ---- errors ------------------------------------------------------------------------- */
 /* replaces: Python `raise Exception(...)` in coreEngine.py:12-14,20,26 */
@@ -53,6 +57,9 @@ int adas_engine_destroy(adas_engine* e);
  * in_shape4 = [N(=1), C, H, W].  out_shapes: n_out rows of 4 int64 (unused dims = 0),
  * out_ranks[n_out].  Shapes are per batch-1 like the reference bindings. */
 int adas_engine_model_kind(const adas_engine* e, int* kind);
+/* plan header meta word `idx` (0..15): YOLO [0] = classes, [1] = anchors, [2] = lite head (YOLOV5_LITE);
+ * UFLD [0..5] = grid / class-row / lane dims, [6] = dataset (0 CULane, 1 TuSimple), see csrc/plan.h */
+int adas_engine_meta(const adas_engine* e, int idx, int* value);
 int adas_engine_input_shape(const adas_engine* e, int64_t in_shape4[4]);
 int adas_engine_num_outputs(const adas_engine* e, int* n_out);
 int adas_engine_output_shape(const adas_engine* e, int idx, int64_t shape4[4], int* rank);

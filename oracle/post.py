@@ -90,11 +90,35 @@ def ufld_prepare_input(img_bgr: np.ndarray, in_h: int, in_w: int, crop_ratio: fl
 # ---------------------------------------------------------------------------------------------
 # YOLO post-processing
 # ---------------------------------------------------------------------------------------------
+V5_ANCHORS = np.asarray([[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]], np.float32).reshape(3, -1, 2)
+
+
+def yolo_lite_postprocess(outs: np.ndarray, in_hw=(640, 640)) -> np.ndarray:
+    """YoloLiteParameters.lite_postprocess, yoloDetector.py:36-50 (model_type == YOLOV5_LITE): grid / anchor decode of a
+    sigmoid-only head [A, 5+nc], float32, one rounding per numpy op.  grid = __make_grid(w, h) -> row r is (r % h, r // h)
+    (np.meshgrid(arange(ny=h), arange(nx=w)), :31-33).  Returns a decoded copy (the reference works in place)."""
+    outs = np.array(outs, np.float32)
+    row = 0
+    for i, stride in enumerate((8, 16, 32)):
+        h, w = int(in_hw[0] / stride), int(in_hw[1] / stride)
+        n = 3 * h * w
+        r = np.arange(w * h)
+        grid = np.stack((r % h, r // h), 1).astype(np.float32)
+        xy = outs[row:row + n, 0:2]
+        outs[row:row + n, 0:2] = (xy * np.float32(2.0) - np.float32(0.5) + np.tile(grid, (3, 1))) * np.float32(stride)
+        wh = outs[row:row + n, 2:4] * np.float32(2.0)
+        outs[row:row + n, 2:4] = wh * wh * np.repeat(V5_ANCHORS[i], h * w, axis=0)
+        row += n
+    return outs
+
+
 def yolo_process_output(raw: np.ndarray, kind: str, box_score: float):
-    """YoloDetector.__process_output, yoloDetector.py:104-133, vectorised.  raw: [4+nc, A] (v8) or [A, 5+nc] (v5).
+    """YoloDetector.__process_output, yoloDetector.py:104-133, vectorised.  raw: [4+nc, A] (v8) or [A, 5+nc] (v5, v5lite).
     Returns boxes xyxy float32 [N,4], class ids int [N], confs list[float] in ascending anchor order."""
     out = raw.T if kind == "v8" else raw
     out = np.asarray(out, np.float32)
+    if kind == "v5lite":
+        out = yolo_lite_postprocess(out)
     probs = out[:, 4:] if kind == "v8" else out[:, 5:] * out[:, 4:5]
     cls = np.argmax(probs, axis=1)
     conf = probs[np.arange(out.shape[0]), cls]

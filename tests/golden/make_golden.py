@@ -89,6 +89,31 @@ def gen_yolo():
     print("yolo cases", [(k, v.shape) for k, v in res.items() if k.endswith("_box")])
 
 
+def gen_yolo_lite():
+    """ObjectModelType.YOLOV5_LITE: the reference's own lite_postprocess + __process_output + NMS on a sigmoid-only head."""
+    res = {}
+    holder = [None]
+    det = make_yolo(ObjectModelType.YOLOV5_LITE, holder)
+    names = det.class_names
+    for seed in (20, 21, 22):
+        for (h, w) in ((720, 1280), (480, 640)) if seed == 20 else ((720, 1280),):
+            holder[0] = synth.yolo_v5_lite_head(seed)          # DetectFrame decodes in place: fresh tensor per call
+            fr = synth.frame(seed, h, w)
+            det.DetectFrame(fr)
+            info = det._object_info
+            key = f"v5lite_s{seed}_{h}x{w}"
+            res[key + "_box"] = np.array([[i.x, i.y, i.width, i.height] for i in info], np.float32).reshape(-1, 4)
+            res[key + "_conf"] = np.array([i.conf for i in info], np.float64)
+            res[key + "_cls"] = np.array([names.index(i.label) for i in info], np.int32)
+    # the decoded tensor itself (lite_postprocess alone), sampled
+    lite = ymod.YoloLiteParameters(ObjectModelType.YOLOV5_LITE, [1, 3, 640, 640], 80)
+    dec = lite.lite_postprocess(synth.yolo_v5_lite_head(20).copy())
+    res["decoded_s20_sha"] = np.frombuffer(bytes.fromhex(sha(dec)), np.uint8)
+    res["decoded_s20_sample"] = dec[::97, :6].copy()
+    np.savez_compressed(os.path.join(OUT, "yolo_lite.npz"), **res)
+    print("yolo lite cases", [(k, v.shape) for k, v in res.items() if k.endswith("_box")])
+
+
 def gen_ufld():
     res = {}
     holder = [None]
@@ -207,8 +232,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "birdview":
         gen_birdview()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "lite":
+        gen_yolo_lite()
+        sys.exit(0)
     gen_nms()
     gen_yolo()
+    gen_yolo_lite()
     gen_ufld()
     gen_track()
     gen_ufld_net_pin()

@@ -52,6 +52,32 @@ def yolo_v5_head(seed: int, n_hot: int = 100, nc: int = 80, A: int = 25200) -> n
     return out
 
 
+def yolo_v5_lite_head(seed: int, n_hot: int = 100, nc: int = 80, in_hw=(640, 640)) -> np.ndarray:
+    """[A, 5+nc] float32 SIGMOID-ONLY v5 rows (all values in (0,1)) as a YOLOv5-lite export emits them: the grid / anchor
+    decode is left to YoloLiteParameters.lite_postprocess.  Hot rows decode to ~100 px boxes near shared centres."""
+    rng = np.random.default_rng(seed)
+    A = sum(3 * (in_hw[0] // s) * (in_hw[1] // s) for s in (8, 16, 32))
+    out = np.empty((A, 5 + nc), np.float32)
+    out[:, 0:4] = rng.uniform(0.05, 0.95, (A, 4))
+    out[:, 4] = rng.uniform(0, 0.3, A)
+    out[:, 5:] = rng.uniform(0, 0.2, (A, nc))
+    hot = rng.choice(A, n_hot, replace=False)
+    for a in hot:
+        out[a, 2:4] = rng.uniform(0.55, 0.95, 2)
+        out[a, 4] = rng.uniform(0.7, 0.99)
+        out[a, 5 + rng.integers(0, nc)] = rng.uniform(0.6, 0.99)
+    # clusters: neighbouring grid cells of one level fire together (overlapping boxes for the NMS)
+    base = 3 * 80 * 80 + 40 * 40            # level 1 (stride 16), anchor 1
+    for k, cell in enumerate(rng.choice(40 * 38, 12, replace=False)):
+        for d in (0, 1, 40):
+            a = base + cell + d
+            out[a, 0:2] = rng.uniform(0.3, 0.7, 2)
+            out[a, 2:4] = rng.uniform(0.6, 0.8, 2)
+            out[a, 4] = rng.uniform(0.75, 0.99)
+            out[a, 5 + (k % nc)] = rng.uniform(0.7, 0.99)
+    return out
+
+
 def ufld_heads(seed: int, ngr=200, ncr=72, ngc=100, ncc=81, nl=4, invalid_lanes=()):
     """4 head tensors [1,...] float32: loc ~ N(0,3) with a smooth ridge, exist logits mostly valid."""
     rng = np.random.default_rng(seed)

@@ -172,6 +172,40 @@ def test_engine_protocol_and_detector_api(tmp_path):
         UltrafastLaneDetectorV2(upath, LaneModelType.UFLDV2_CURVELANES, None)
 
 
+def test_yolov5_lite_plan_matches_decoded_plan():
+    """ObjectModelType.YOLOV5_LITE end to end: a lite plan (sigmoid-only head + device lite_postprocess) gives the detections of the
+    plan whose Detect layer decodes in the graph, bit for bit; engine_inference on the lite plan returns the UNdecoded tensor whose host
+    lite_postprocess (oracle restatement of yoloDetector.py:36-50) reproduces the fused call; the model_type / plan pairing is enforced."""
+    from adas_b200.ObjectDetector import YoloDetector, ObjectModelType
+    path, sd, _ = cached_plan("yolov5", scale="n")
+    lpath, _, _ = cached_plan("yolov5", scale="n", lite=True)
+    cfg = {"classes_path": None, "box_score": 0.4, "box_nms_iou": 0.45}
+    YoloDetector.set_defaults({"model_path": path, "model_type": ObjectModelType.YOLOV5, **cfg})
+    det = YoloDetector(logger=None, max_batch=2)
+    YoloDetector.set_defaults({"model_path": lpath, "model_type": ObjectModelType.YOLOV5_LITE, **cfg})
+    det_l = YoloDetector(logger=None, max_batch=2)
+    frames = [synth.frame(3), synth.frame(4)]
+    a, b = det.DetectFrames(frames), det_l.DetectFrames(frames)
+    key = lambda rs: [(r.x, r.y, r.width, r.height, r.conf, r.label) for r in rs]
+    assert sum(len(x) for x in a) > 0
+    for ra, rb in zip(a, b):
+        assert key(ra) == key(rb)
+    # raw tensors: same logits, decoded vs sigmoid-only boxes
+    x = _blob(frames)
+    raw, raw_l = det.engine.engine_inference(x)[0], det_l.engine.engine_inference(x)[0]
+    assert np.array_equal(raw[..., 4:], raw_l[..., 4:]) and raw_l[..., :4].max() <= 1.0 and raw[..., :4].max() > 1.0
+    for i in range(2):
+        assert np.array_equal(post.yolo_lite_postprocess(raw_l[i]), raw[i])
+        r = post.yolo_postprocess(raw_l[i], "v5lite", post.letterbox_geom(720, 1280, 640, 640), 0.4, 0.45)
+        assert np.array_equal(np.array([[q.x, q.y, q.width, q.height] for q in b[i]], np.float32).reshape(-1, 4), r["boxes"])
+    YoloDetector.set_defaults({"model_path": path, "model_type": ObjectModelType.YOLOV5_LITE, **cfg})
+    with pytest.raises(Exception):
+        YoloDetector(logger=None)            # lite model_type on a decoded plan
+    YoloDetector.set_defaults({"model_path": lpath, "model_type": ObjectModelType.YOLOV5, **cfg})
+    with pytest.raises(Exception):
+        YoloDetector(logger=None)
+
+
 @pytest.mark.parametrize("impl", ["native", "python"])
 def test_bytetracker_matches_reference_golden(golden_dir, impl):
     from adas_b200.ObjectTracker import BYTETracker, BYTETrackerPy

@@ -57,6 +57,23 @@ def test_yolo_post_matches_reference_golden(golden_dir):
         _check_yolo(res, b, g[k + "_box"], g[k + "_conf"], g[k + "_cls"])
 
 
+def test_yolo_lite_post_matches_reference_golden(golden_dir):
+    """ObjectModelType.YOLOV5_LITE.  The device lite_postprocess + select + NMS on the sigmoid-only head equals the
+    reference's own YoloDetector(model_type=YOLOV5_LITE) bit for bit (golden vectors made by tests/golden/make_golden.py lite)."""
+    g = np.load(os.path.join(golden_dir, "yolo_lite.npz"))
+    seeds = (20, 21, 22)
+    raw = np.stack([synth.yolo_v5_lite_head(s) for s in seeds])
+    res = _capi.yolo_postprocess(raw, 3, 80, (640, 640), (720, 1280), 0.4, 0.45)          # 3 = ADAS_MODEL_YOLOV5_LITE
+    for b, s in enumerate(seeds):
+        k = f"v5lite_s{s}_720x1280"
+        _check_yolo(res, b, g[k + "_box"], g[k + "_conf"], g[k + "_cls"])
+    res = _capi.yolo_postprocess(raw[:1], 3, 80, (640, 640), (480, 640), 0.4, 0.45)
+    _check_yolo(res, 0, g["v5lite_s20_480x640_box"], g["v5lite_s20_480x640_conf"], g["v5lite_s20_480x640_cls"])
+    # the same tensor through the non-lite kind must NOT match (the decode really happens on the device)
+    res5 = _capi.yolo_postprocess(raw[:1], 1, 80, (640, 640), (720, 1280), 0.4, 0.45)
+    assert int(res5[4][0]) != len(g["v5lite_s20_720x1280_box"]) or not np.array_equal(res5[0][0, :int(res5[4][0])], g["v5lite_s20_720x1280_box"])
+
+
 @pytest.mark.parametrize("n_hot,thr,iou", [(0, 0.4, 0.45), (1, 0.4, 0.45), (2, 0.4, 0.5), (300, 0.4, 0.45), (900, 0.25, 0.3), (120, 0.6, 0.7)])
 def test_yolo_post_vs_oracle_edge_cases(n_hot, thr, iou):
     raw = np.stack([synth.yolo_v8_head(50 + s, n_hot=n_hot) for s in range(3)])

@@ -73,3 +73,25 @@ def test_association_matches_reference(golden_dir):
         for nm, c, th in (("iou", cost, 0.5), ("fuse", fused, 0.8), ("fuse7", fused, 0.7)):
             x, _, _ = post.lapjv_extended(c, th)
             assert np.array_equal(x, g[f"assoc{k}_{nm}_x"]), (k, nm)
+
+
+@pytest.mark.parametrize("key", ["v5lite_s20_720x1280", "v5lite_s20_480x640", "v5lite_s21_720x1280", "v5lite_s22_720x1280"])
+def test_yolo_lite_post_matches_reference(golden_dir, key):
+    """ObjectModelType.YOLOV5_LITE -- lite_postprocess (yoloDetector.py:36-50) + __process_output + NMS, golden vectors
+    from the reference's own YoloDetector on a sigmoid-only head."""
+    g = np.load(os.path.join(golden_dir, "yolo_lite.npz"))
+    seed = int(key.split("_")[1][1:])
+    h, w = [int(v) for v in key.split("_")[2].split("x")]
+    raw = synth.yolo_v5_lite_head(seed)
+    r = post.yolo_postprocess(raw, "v5lite", post.letterbox_geom(h, w, 640, 640), 0.4, 0.45)
+    assert np.array_equal(r["boxes"], g[key + "_box"])
+    assert np.array_equal(r["scores"].astype(np.float64), g[key + "_conf"])
+    assert np.array_equal(r["cls"], g[key + "_cls"])
+    assert len(r["idx"]) != len(set(r["idx"].tolist())) or len(r["idx"]) < r["n_cand"]       # the NMS really suppresses / duplicates
+
+
+def test_yolo_lite_decode_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "yolo_lite.npz"))
+    dec = post.yolo_lite_postprocess(synth.yolo_v5_lite_head(20))
+    assert np.array_equal(_sha(dec), g["decoded_s20_sha"])
+    assert np.array_equal(dec[::97, :6], g["decoded_s20_sample"])

@@ -4,7 +4,9 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert
 import numpy as np
 import adas_b200
 from adas_b200 import _capi, plan
-LAYERS = [  # name, B, cin, cout, H, W, k
+LAYERS = [
+    ("P3 1x1 1024->256 80x80", 8, 1024, 256, 80, 80, 1),
+    ("P4 1x1 2048->512 40x40", 8, 2048, 512, 40, 40, 1),  # name, B, cin, cout, H, W, k
     ("P3 3x3 128->128 80x80", 8, 128, 128, 80, 80, 3),
     ("P4 3x3 256->256 40x40", 8, 256, 256, 40, 40, 3),
     ("P5 3x3 256->256 20x20", 8, 256, 256, 20, 20, 3),

@@ -44,6 +44,16 @@ class YoloDetector(ObjectDetectBase):
             self.logger.info(f"YoloDetector Type : [{self.engine.framework_type}] || Version : [{self.engine.providers}]")
         self.set_input_details(self.engine)
         self.set_output_details(self.engine)
+        # model_type <-> plan consistency (the reference trusts the user; a wrong pairing silently decodes boxes twice or never)
+        kind, meta = self.engine.handle.model_kind, self.engine.handle.meta
+        want_v8 = self.model_type in (ObjectModelType.YOLOV8, ObjectModelType.YOLOV9)
+        if want_v8 != (kind == 0):
+            raise Exception(f"model_type {self.model_type} does not match the plan (kind {kind})")
+        is_lite = kind == 1 and meta[2] != 0
+        if (self.model_type == ObjectModelType.YOLOV5_LITE) != is_lite:
+            raise Exception(f"model_type {self.model_type} needs a {'lite ' if not is_lite else 'non-lite '}YOLOv5 plan (plan.build_yolov5(lite=...))")
+        if self.model_type in (ObjectModelType.YOLOV10, ObjectModelType.EfficientDet):
+            raise Exception(f"{self.model_type} heads are not packed by adas_b200.plan")
 
     def _initialize_class(self, classes_path) -> None:
         if classes_path is None:      # synthetic runs: COCO-sized anonymous label list

@@ -19,7 +19,7 @@ _lib = None
 # every symbol include/adas_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "adas_last_error", "adas_version", "adas_launch_count", "adas_engine_create", "adas_engine_destroy",
-    "adas_engine_model_kind", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
+    "adas_engine_model_kind", "adas_engine_meta", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
@@ -122,6 +122,10 @@ class Engine:
         k = C.c_int()
         check(lib().adas_engine_model_kind(self._h, C.byref(k)))
         self.model_kind = k.value
+        self.meta = []
+        for i in range(16):
+            check(lib().adas_engine_meta(self._h, i, C.byref(k)))
+            self.meta.append(int(k.value))
         s = (C.c_int64 * 4)()
         check(lib().adas_engine_input_shape(self._h, s))
         self.input_shape = [int(v) for v in s]

@@ -129,8 +129,9 @@ int launch_ufld_pre(const uint8_t* frames, int B, int H, int W, int in_h, int in
 struct YoloLevel { const float* ptr; int ld; int H, W; int stride; int rows_per_img; };
 int launch_yolov8_head_decode(const YoloLevel* lv /*3*/, int B, int nc, float* raw /*[B,4+nc,A]*/, int A,
                               cudaStream_t st);
-int launch_yolov5_head_decode(const YoloLevel* lv /*3*/, int B, int nc, float* raw /*[B,A,5+nc]*/, int A,
+int launch_yolov5_head_decode(const YoloLevel* lv /*3*/, int B, int nc, float* raw /*[B,A,5+nc]*/, int A, int lite,
                               cudaStream_t st);
+int launch_yolov5_lite_post(float* raw /*[B,A,5+nc], in place*/, int B, int A, int nc, int in_h, int in_w, cudaStream_t st);
 struct YoloPostBufs {
     // device scratch, sized for max_batch
     int32_t* flags;      // [B, A] candidate flag

@@ -435,7 +435,13 @@ static int head_decode(adas_engine* e, int batch) {
     }
     const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
     if (e->hdr.model_kind == ADAS_MODEL_YOLOV8) return launch_yolov8_head_decode(lv, batch, nc, e->d_raw, A, e->stream);
-    return launch_yolov5_head_decode(lv, batch, nc, e->d_raw, A, e->stream);
+    return launch_yolov5_head_decode(lv, batch, nc, e->d_raw, A, (int)e->hdr.meta[2], e->stream);
+}
+// YOLOV5_LITE plans (meta[2] != 0): the network output is the sigmoid-only head; the fused detect calls apply
+// YoloLiteParameters.lite_postprocess (yoloDetector.py:36-50) on the device before candidate selection.
+static int lite_post(adas_engine* e, int batch) {
+    if (e->hdr.model_kind != ADAS_MODEL_YOLOV5 || e->hdr.meta[2] == 0) return 0;
+    return launch_yolov5_lite_post(e->d_raw, batch, (int)e->hdr.meta[1], (int)e->hdr.meta[0], (int)e->hdr.in_h, (int)e->hdr.in_w, e->stream);
 }
 
 static int alloc_yolo_post(YoloPostBufs* w, int B, int A, int max_det) {
@@ -605,6 +611,11 @@ int adas_engine_destroy(adas_engine* e) {
 }
 
 int adas_engine_model_kind(const adas_engine* e, int* kind) { *kind = (int)e->hdr.model_kind; return 0; }
+int adas_engine_meta(const adas_engine* e, int idx, int* value) {
+    ADAS_CHECK(e != nullptr && idx >= 0 && idx < 16 && value != nullptr, "adas_engine_meta: bad index %d", idx);
+    *value = (int)e->hdr.meta[idx];
+    return 0;
+}
 int adas_engine_input_shape(const adas_engine* e, int64_t s[4]) {
     s[0] = 1; s[1] = e->hdr.in_c; s[2] = e->hdr.in_h; s[3] = e->hdr.in_w;
     return 0;
@@ -704,6 +715,7 @@ int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     if (run_plan(e, batch)) return 1;
     tr.mark("plan");
     if (head_decode(e, batch)) return 1;
+    if (lite_post(e, batch)) return 1;
     tr.mark("decode");
     if (launch_yolo_post(e->d_raw, (int)e->hdr.model_kind, batch, A, nc, g, box_score, nms_iou, max_det, e->yp, e->stream)) return 1;
     tr.mark("select+nms");
@@ -717,6 +729,7 @@ int adas_yolo_postprocess(int device, const float* raw_host, int model_kind, int
                           int in_w, int src_h, int src_w, double box_score, double nms_iou, int max_det, float* boxes_xywh,
                           float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts, int32_t* n_candidates) {
     ADAS_CUDA(cudaSetDevice(device));
+    ADAS_CHECK(model_kind == ADAS_MODEL_YOLOV8 || model_kind == ADAS_MODEL_YOLOV5 || model_kind == ADAS_MODEL_YOLOV5_LITE, "adas_yolo_postprocess: bad model kind %d", model_kind);
     const size_t per = model_kind == ADAS_MODEL_YOLOV8 ? (size_t)(4 + n_classes) * n_anchors : (size_t)n_anchors * (5 + n_classes);
     float* d_raw = nullptr;
     ADAS_CUDA(cudaMalloc(&d_raw, (size_t)batch * per * 4));
@@ -724,6 +737,10 @@ int adas_yolo_postprocess(int device, const float* raw_host, int model_kind, int
     YoloPostBufs w{};
     int rc = alloc_yolo_post(&w, batch, n_anchors, max_det);
     const LetterboxGeom g = letterbox_geom(src_h, src_w, in_h, in_w);
+    if (!rc && model_kind == ADAS_MODEL_YOLOV5_LITE) {       // raw is the sigmoid-only head of a lite export: lite_postprocess first
+        rc = launch_yolov5_lite_post(d_raw, batch, n_anchors, n_classes, in_h, in_w, 0);
+        model_kind = ADAS_MODEL_YOLOV5;
+    }
     if (!rc) rc = launch_yolo_post(d_raw, model_kind, batch, n_anchors, n_classes, g, box_score, nms_iou, max_det, w, 0);
     if (!rc) rc = copy_yolo_results(w, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, n_candidates, 0);
     free_yolo_post(&w);
@@ -821,6 +838,7 @@ int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames
     if (run_plan(e, batch)) return 1;
     if (run_plan(ufld, batch)) return 1;
     if (head_decode(e, batch)) return 1;
+    if (lite_post(e, batch)) return 1;
     if (launch_yolo_post(e->d_raw, (int)e->hdr.model_kind, batch, A, nc, g, box_score, nms_iou, max_det, e->yp, e->stream)) return 1;
     if (copy_yolo_results_enqueue(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, e->h_ncand.data(), e->stream)) return 1;
     {

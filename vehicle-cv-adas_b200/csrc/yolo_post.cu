@@ -64,7 +64,8 @@ int launch_yolov8_head_decode(const YoloLevel* lv, int B, int nc, float* raw, in
 // raw[b][idx][5+nc], idx = level offset + anchor*H*W + y*W + x  (yoloDetector.py:45-48 ordering).
 __constant__ float c_v5_anchors[18] = {10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326};
 
-__global__ void yolov5_decode_kernel(YoloLevel l0, YoloLevel l1, YoloLevel l2, int B, int nc, float* __restrict__ raw, int A) {
+// lite != 0: the head of a YOLOv5-lite export -- sigmoid only, grid/anchor decode left to lite_postprocess (yoloDetector.py:36-50).
+__global__ void yolov5_decode_kernel(YoloLevel l0, YoloLevel l1, YoloLevel l2, int B, int nc, float* __restrict__ raw, int A, int lite) {
     const long long total = (long long)B * A;
     const int no = 5 + nc;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -82,18 +83,61 @@ __global__ void yolov5_decode_kernel(YoloLevel l0, YoloLevel l1, YoloLevel l2, i
         const float st = (float)lv.stride;
         const float sx = 1.f / (1.f + expf(-p[0])), sy = 1.f / (1.f + expf(-p[1]));
         const float sw = 1.f / (1.f + expf(-p[2])), sh = 1.f / (1.f + expf(-p[3]));
-        o[0] = (sx * 2.f - 0.5f + (float)x) * st;
-        o[1] = (sy * 2.f - 0.5f + (float)y) * st;
-        o[2] = (sw * 2.f) * (sw * 2.f) * c_v5_anchors[li * 6 + an * 2];
-        o[3] = (sh * 2.f) * (sh * 2.f) * c_v5_anchors[li * 6 + an * 2 + 1];
+        if (lite) { o[0] = sx; o[1] = sy; o[2] = sw; o[3] = sh; }
+        else {
+            o[0] = (sx * 2.f - 0.5f + (float)x) * st;
+            o[1] = (sy * 2.f - 0.5f + (float)y) * st;
+            o[2] = (sw * 2.f) * (sw * 2.f) * c_v5_anchors[li * 6 + an * 2];
+            o[3] = (sh * 2.f) * (sh * 2.f) * c_v5_anchors[li * 6 + an * 2 + 1];
+        }
         for (int k = 4; k < no; ++k) o[k] = 1.f / (1.f + expf(-p[k]));
     }
 }
 
-int launch_yolov5_head_decode(const YoloLevel* lv, int B, int nc, float* raw, int A, cudaStream_t st) {
+int launch_yolov5_head_decode(const YoloLevel* lv, int B, int nc, float* raw, int A, int lite, cudaStream_t st) {
     const long long total = (long long)B * A;
     int blocks = (int)((total + 127) / 128);
-    yolov5_decode_kernel<<<blocks, 128, 0, st>>>(lv[0], lv[1], lv[2], B, nc, raw, A);
+    yolov5_decode_kernel<<<blocks, 128, 0, st>>>(lv[0], lv[1], lv[2], B, nc, raw, A, lite);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// YoloLiteParameters.lite_postprocess (yoloDetector.py:36-50), in place on raw[b][idx][5+nc] like the reference: rows are ordered
+// level -> anchor -> grid cell; per level h = int(in_h / stride), w = int(in_w / stride), grid = __make_grid(w, h) whose row r is
+// (r % h, r // h) (np.meshgrid(arange(ny = h), arange(nx = w)) -- identical to (x, y) only for square inputs; kept as the reference
+// computes it).  float32 arithmetic, one rounding per numpy op: xy = ((v * 2) - 0.5 + g) * stride ; wh = ((v * 2) ** 2) * anchor.
+__global__ void yolov5_lite_post_kernel(float* __restrict__ raw, int B, int A, int nc, int in_h, int in_w) {
+    const long long total = (long long)B * A;
+    const int no = 5 + nc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int a = (int)(i % A);
+        int li = 0, h = 0, w = 0, stride = 8;
+        for (li = 0; li < 3; ++li) {
+            stride = 8 << li;
+            h = in_h / stride; w = in_w / stride;
+            if (a < 3 * h * w) break;
+            a -= 3 * h * w;
+        }
+        if (li == 3) continue;              // rows past the three levels (never produced by a v5 head)
+        const int hw = h * w;
+        const int an = a / hw;
+        const int r = a - an * hw;
+        const float gx = (float)(r % h), gy = (float)(r / h);
+        float* o = raw + (size_t)i * no;
+        const float st = (float)stride;
+        o[0] = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(o[0], 2.f), 0.5f), gx), st);
+        o[1] = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(o[1], 2.f), 0.5f), gy), st);
+        const float tw = __fmul_rn(o[2], 2.f), th = __fmul_rn(o[3], 2.f);
+        o[2] = __fmul_rn(__fmul_rn(tw, tw), c_v5_anchors[li * 6 + an * 2]);
+        o[3] = __fmul_rn(__fmul_rn(th, th), c_v5_anchors[li * 6 + an * 2 + 1]);
+    }
+}
+
+int launch_yolov5_lite_post(float* raw, int B, int A, int nc, int in_h, int in_w, cudaStream_t st) {
+    const long long total = (long long)B * A;
+    int blocks = (int)((total + 127) / 128);
+    yolov5_lite_post_kernel<<<blocks, 128, 0, st>>>(raw, B, A, nc, in_h, in_w);
     count_launch();
     ADAS_CUDA(cudaGetLastError());
     return 0;

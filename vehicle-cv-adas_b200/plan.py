@@ -428,7 +428,10 @@ def build_yolov8(weights: Weights, scale: str = "l", nc: int = 80, in_h: int = 6
 YOLOV5_SCALES = {"n": (0.33, 0.25), "s": (0.33, 0.50), "m": (0.67, 0.75), "l": (1.0, 1.0), "x": (1.33, 1.25)}
 
 
-def build_yolov5(weights: Weights, scale: str = "n", nc: int = 80, in_h: int = 640, in_w: int = 640) -> PlanBuilder:
+def build_yolov5(weights: Weights, scale: str = "n", nc: int = 80, in_h: int = 640, in_w: int = 640, lite: bool = False) -> PlanBuilder:
+    """lite=True packs a YOLOv5-lite style head: the engine output is the sigmoid-only tensor and the grid / anchor decode is
+    `YoloLiteParameters.lite_postprocess` (reference yoloDetector.py:36-50, ObjectModelType.YOLOV5_LITE), run on the device by the
+    fused detect calls.  Header meta[2] marks such plans."""
     depth, width = YOLOV5_SCALES[scale]
     ch = lambda c: int(math.ceil(c * width / 8) * 8)
     rep = lambda n: max(round(n * depth), 1)
@@ -492,6 +495,7 @@ def build_yolov5(weights: Weights, scale: str = "n", nc: int = 80, in_h: int = 6
         pb.outputs.append((head.buf, 0, head.C, stride))
         A += 3 * feat.H * feat.W
     pb.meta[0], pb.meta[1] = nc, A
+    pb.meta[2] = 1 if lite else 0
     return pb
 
 

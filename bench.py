@@ -64,7 +64,7 @@ def build_plans(seed: int = 0):
     out = {}
     for kind, builder, kw in (("yolov8", plan.build_yolov8, dict(scale="l")), ("ufldv2", plan.build_ufldv2, dict(backbone="34"))):
         path = os.path.join(CACHE, f"bench_{kind}_s{seed}.b200w")
-        W = plan.synth_weights(kind, seed)
+        W = plan.synth_weights(kind, seed, variant=kw.get("scale", kw.get("backbone")))
         pb = builder(W, **kw)
         if not os.path.isfile(path):
             pb.write(path + f".{os.getpid()}.tmp")

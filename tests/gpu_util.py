@@ -34,7 +34,8 @@ def cached_plan(kind: str, seed: int = 0, **kw):
     os.makedirs(CACHE, exist_ok=True)
     tag = kind + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items())) + f"_s{seed}"
     path = os.path.join(CACHE, tag + ".b200w")
-    W = plan.synth_weights({"yolov8": "yolov8", "yolov5": "yolov5", "ufldv2": "ufldv2"}[kind], seed)
+    variant = kw.get("scale", kw.get("backbone"))             # calibrated BatchNorm statistics exist for the tested variants
+    W = plan.synth_weights(kind, seed, variant=variant)
     if kind == "yolov8":
         pb = plan.build_yolov8(W, **kw)
     elif kind == "yolov5":

@@ -25,7 +25,7 @@ class YoloDetector(ObjectDetectBase):
         "box_score": 0.4,
         "box_nms_iou": 0.45,
     }
-    MAX_DET = 300
+    MAX_DET = 1024         # output arrays per frame; the library fails loudly if more detections survive the NMS
 
     def __init__(self, logger=None, **kwargs):
         ObjectDetectBase.__init__(self, logger)

@@ -206,7 +206,7 @@ class Engine:
         arr = (C.POINTER(C.c_float) * len(out_ptrs))(*[C.cast(C.c_void_p(p), C.POINTER(C.c_float)) for p in out_ptrs])
         check(lib().adas_engine_infer_dev(self._h, C.cast(C.c_void_p(x_ptr), C.POINTER(C.c_float)), batch, arr))
 
-    def yolo_detect(self, frames, box_score: float, nms_iou: float, max_det: int = 300, on_device: bool = False, shape=None):
+    def yolo_detect(self, frames, box_score: float, nms_iou: float, max_det: int = 1024, on_device: bool = False, shape=None):
         """frames: uint8 [B,H,W,3] numpy (host) or (device pointer, (B,H,W)) when on_device."""
         if on_device:
             ptr, (B, H, W) = frames, shape
@@ -244,7 +244,7 @@ class Engine:
         return pts, npts, status, coords
 
 
-def detect_pair(yolo: "Engine", ufld: "Engine", frames, box_score: float, nms_iou: float, max_det: int = 300, on_device: bool = False, shape=None):
+def detect_pair(yolo: "Engine", ufld: "Engine", frames, box_score: float, nms_iou: float, max_det: int = 1024, on_device: bool = False, shape=None):
     """One library call: YOLO detect then UFLD lane detect on the same frames -> (yolo tuple, ufld tuple)."""
     if on_device:
         ptr, (B, H, W) = frames, shape
@@ -270,7 +270,7 @@ def detect_pair(yolo: "Engine", ufld: "Engine", frames, box_score: float, nms_io
 
 
 def yolo_postprocess(raw: np.ndarray, model_kind: int, n_classes: int, in_hw, src_hw, box_score: float, nms_iou: float,
-                     max_det: int = 300, device: int = 0):
+                     max_det: int = 1024, device: int = 0):
     raw = as_c(raw, np.float32)
     B = raw.shape[0]
     A = raw.shape[2] if model_kind == 0 else raw.shape[1]

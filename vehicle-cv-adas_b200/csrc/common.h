@@ -109,6 +109,8 @@ int launch_upsample2x(const __half* in, int in_ld, int B, int H, int W, int C, _
                       cudaStream_t st);
 int launch_layernorm(const __half* in, int in_ld, int rows, int d_len, int d_norm, const float* gamma,
                      const float* beta, float eps, __half* out, int out_ld, cudaStream_t st);
+int launch_fc_stream(const __half* x, int x_ld, int batch, const __half* W, int K, int N, const float* bias, int act, void* out, int out_ld,
+                     int out_f32, cudaStream_t st);
 int launch_nchw_to_padded(const float* in, int B, int C, int H, int W, __half* out, int out_ld, cudaStream_t st);
 int launch_stempack(const __half* img, int B, int H, int W, __half* q, cudaStream_t st);
 int launch_zero_rows(__half* buf, int ld, int C, int row0, int nrows, cudaStream_t st);

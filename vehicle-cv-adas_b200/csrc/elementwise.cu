@@ -297,3 +297,95 @@ int launch_zero_rows(__half* buf, int ld, int C, int row0, int nrows, cudaStream
 }
 
 }  // namespace adas
+
+namespace adas {
+// ---- fully connected layer at small batch: weight-streaming kernel ------------------------------------------------------------
+// Replaces the first Linear of the UFLDv2 head (exportLib/ultrafastLaneV2/model_culane.py:35-37, `cls` Sequential) at the batch
+// sizes the pipeline uses: out[b][n] = act(bias[n] + sum_k x[b][k] * W[n][k]).  At batch <= 32 the layer is a stream of the
+// weight matrix (FC1: 2048 x 4992 fp16 = 20 MB, L2-resident): the swap-AB tensor-core GEMM had 8 CTAs for it (47.8 us, 0.43 TB/s).
+// One warp owns FC_F output features and 8 batch rows; lanes stride over K in 16-byte chunks, fp32 accumulation, fixed xor-shuffle
+// reduction.  Every (b, n) value is computed by the same instruction sequence whatever the batch size (batch rows are independent
+// accumulators), so per-frame results do not depend on the batch.
+static constexpr int FC_F = 4;          // features per warp
+static constexpr int FC_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * FC_WARPS)
+fc_stream_kernel(const __half* __restrict__ x, int x_ld, int batch, const __half* __restrict__ W, int K, int N, const float* __restrict__ bias,
+                 int act, void* __restrict__ out, int out_ld, int out_f32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = (blockIdx.x * FC_WARPS + warp) * FC_F;
+    const int b0 = blockIdx.y * 8;
+    if (n0 >= N) return;
+    float acc[FC_F][8];
+#pragma unroll
+    for (int f = 0; f < FC_F; ++f)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[f][b] = 0.f;
+    const int nb = min(8, batch - b0);
+    for (int k = lane * 8; k < K; k += 32 * 8) {
+        uint4 w4[FC_F];
+#pragma unroll
+        for (int f = 0; f < FC_F; ++f) {
+            const int n = min(n0 + f, N - 1);
+            w4[f] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)n * K + k));
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < nb) {
+                const uint4 x4 = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(b0 + b) * x_ld + k));
+                const __half2* xh = reinterpret_cast<const __half2*>(&x4);
+                float2 xf[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xf[j] = __half22float2(xh[j]);
+#pragma unroll
+                for (int f = 0; f < FC_F; ++f) {
+                    const __half2* wh = reinterpret_cast<const __half2*>(&w4[f]);
+                    float a = acc[f][b];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 wf = __half22float2(wh[j]);
+                        a = fmaf(wf.x, xf[j].x, a);
+                        a = fmaf(wf.y, xf[j].y, a);
+                    }
+                    acc[f][b] = a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < FC_F; ++f)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[f][b] += __shfl_xor_sync(0xffffffffu, acc[f][b], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int f = 0; f < FC_F; ++f) {
+            const int n = n0 + f;
+            if (n >= N) break;
+            const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < nb) {
+                    float v = acc[f][b] + bv;
+                    if (act == 1) v = v / (1.f + __expf(-v));
+                    else if (act == 2) v = fmaxf(v, 0.f);
+                    const size_t o = (size_t)(b0 + b) * out_ld + n;
+                    if (out_f32) reinterpret_cast<float*>(out)[o] = v;
+                    else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
+                }
+            }
+        }
+    }
+}
+
+int launch_fc_stream(const __half* x, int x_ld, int batch, const __half* W, int K, int N, const float* bias, int act, void* out, int out_ld,
+                     int out_f32, cudaStream_t st) {
+    ADAS_CHECK(K % 8 == 0 && x_ld % 8 == 0, "fc_stream: K (%d) and the activation row stride (%d) must be multiples of 8", K, x_ld);
+    dim3 grid((N + FC_WARPS * FC_F - 1) / (FC_WARPS * FC_F), (batch + 7) / 8, 1);
+    fc_stream_kernel<<<grid, 32 * FC_WARPS, 0, st>>>(x, x_ld, batch, W, K, N, bias, act, out, out_ld, out_f32);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // namespace adas

@@ -193,6 +193,20 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     g.out_ld = (int)ob.C;
                 }
                 if (p[17] > 0) g.mt_hint = p[17];       // plan-forced sub-tile count (test hook of plan.py)
+                // Fully connected layers whose weight matrix stays in L2 (FC1 of the UFLD head: 20 MB) run as a weight stream on the CUDA
+                // cores: the swap-AB tensor-core GEMM has only N/256 CTAs for them (profiles/r02_optable_ufld_b8: 47.8 us = 0.43 TB/s).
+                static const bool fc_stream_on = !(getenv("ADAS_B200_FC_STREAM") && getenv("ADAS_B200_FC_STREAM")[0] == '0');
+                if (transposed && e->conv_impl == 0 && fc_stream_on && ntaps == 1 && (size_t)N * Kc * 2 <= ((size_t)48 << 20) && Kc % 8 == 0 && ab.C % 8 == 0) {
+                    const float* bias_p = static_cast<const float*>(tensor_ptr(e, bias_t));
+                    void* out_p = static_cast<uint8_t*>(e->dbufs[out_buf].ptr) + (size_t)out_coff * elem_size(ob.dtype);
+                    const int x_ld = (int)(ab.rows_per_img * ab.C), o_ld = (int)(ob.rows_per_img * ob.C), of32 = ob.dtype == 1 ? 1 : 0;
+                    char d[128];
+                    snprintf(d, sizeof(d), "M=%d N=%d K=%d fc_stream", batch, N, Kc);
+                    prog->step_desc.resize(prog->step_type.size());
+                    prog->step_desc.back() = d;
+                    prog->steps.push_back([=](cudaStream_t st) { return launch_fc_stream(aptr, x_ld, batch, wptr, Kc, N, bias_p, act, out_p, o_ld, of32, st); });
+                    break;
+                }
                 g.Kc = Kc; g.ntaps = ntaps; g.Wp = (int)ab.W + 2; g.kpt = (Kc + 63) / 64; g.BN = BN;
                 g.stages = gemm_tc_pick_stages(BN, ntaps * g.kpt);
                 g.act = act; g.out_f32 = ob.dtype == 1 ? 1 : 0;
@@ -445,7 +459,8 @@ static int lite_post(adas_engine* e, int batch) {
 }
 
 static int alloc_yolo_post(YoloPostBufs* w, int B, int A, int max_det) {
-    w->cap = 1024;
+    w->cap = A;        // every anchor may become a candidate: no limit the reference does not have
+    ADAS_CUDA(cudaMalloc(&w->nms_work, (size_t)B * A * 7 * sizeof(double)));
     ADAS_CUDA(cudaMalloc(&w->flags, (size_t)B * A * 4));
     ADAS_CUDA(cudaMalloc(&w->cls, (size_t)B * A * 4));
     ADAS_CUDA(cudaMalloc(&w->conf, (size_t)B * A * 4));
@@ -461,7 +476,7 @@ static int alloc_yolo_post(YoloPostBufs* w, int B, int A, int max_det) {
     return 0;
 }
 static void free_yolo_post(YoloPostBufs* w) {
-    cudaFree(w->flags); cudaFree(w->cls); cudaFree(w->conf); cudaFree(w->n_cand); cudaFree(w->cand_box); cudaFree(w->cand_conf);
+    cudaFree(w->nms_work); cudaFree(w->flags); cudaFree(w->cls); cudaFree(w->conf); cudaFree(w->n_cand); cudaFree(w->cand_box); cudaFree(w->cand_conf);
     cudaFree(w->cand_cls); cudaFree(w->out_box); cudaFree(w->out_score); cudaFree(w->out_cls); cudaFree(w->out_idx); cudaFree(w->out_count);
     memset(w, 0, sizeof(*w));
 }
@@ -481,8 +496,9 @@ static int copy_yolo_results_finish(const YoloPostBufs& w, int batch, int max_de
     ADAS_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < batch; ++b) {
         if (n_cand) n_cand[b] = nc_host[b];
-        ADAS_CHECK(nc_host[b] <= w.cap, "frame %d: %d candidates exceed the device NMS capacity %d (raise box_score)", b, nc_host[b], w.cap);
-        if (counts[b] > max_det) counts[b] = max_det;
+        // the reference returns every survivor; the caller-sized output arrays hold max_det per frame -- fail loudly instead of
+        // dropping detections silently (advisor finding, r01)
+        ADAS_CHECK(counts[b] <= max_det, "frame %d: %d detections survive the NMS but the output arrays hold %d (raise max_det)", b, counts[b], max_det);
     }
     return 0;
 }

@@ -43,7 +43,9 @@ struct GemmV3 {
     int tma_st;        // staged TMA-store epilogue (fp16, not transposed, BN % 64 == 0)
     int stg_off;       // byte offset of the two staging buffers behind the operand ring
     int pdl;
+    int prefetch_w;    // fetch the first stages' weight tiles before griddepcontrol.wait
     int n_patches;     // stride-2: batch * s2_tw * s2_th
+    FastDiv fd_img, fd_wp, fd_per_img, fd_tw, fd_bw;   // divisors of the epilogue's row arithmetic
 };
 
 struct GemmV3Launch {
@@ -97,63 +99,94 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_holder;
+    // ---- TMA producer pieces (warp 0, lane 0) ----
+    const uint32_t a_bytes = p.s2 ? (uint32_t)(p.s2_bw * p.s2_bh * BK * 2) : (uint32_t)(g.slab ? V3_SLAB_BYTES : A_STAGE_BYTES);
+    const uint32_t tx_bytes = (uint32_t)g.MT * a_bytes + (uint32_t)(taps_per_step * p.BN * BK * 2);
+    const int n_grp = g.slab ? 3 : p.ntaps;              // outer tap groups (slab: dy)
+    const bool dx_inner = (!g.slab && p.ntaps == 9);      // plain 9-tap order is (dy, k-block, dx) too
+    const int o_cnt = dx_inner ? 3 : n_grp;              // outer loop: dy (9-tap plain) or tap group
+    const int i_cnt = dx_inner ? 3 : 1;                  // inner loop: dx (9-tap plain)
+    const int per_img = p.s2_tw * p.s2_th;
+    // weight (B operand) tiles of one pipeline step
+    auto load_b = [&](int grp, int kc, int n0, uint32_t stage, uint32_t fb) {
+        const uint32_t b_dst = smem_base + stage * g.stage_bytes + g.MT * g.a_sub_bytes;
+        if (g.slab) {
+            for (int dx = 0; dx < 3; ++dx) tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
+        } else {
+            tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
+        }
+    };
+    // activation (A operand) tiles of one pipeline step
+    auto load_a = [&](int grp, int kc, int m_t, uint32_t stage, uint32_t fb) {
+        const uint32_t a_dst = smem_base + stage * g.stage_bytes;
+        const int m0 = m_t * BMT;
+        if (g.slab) {
+            const int r0 = m0 + (grp - 1) * p.Wp - 1;
+            for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
+        } else if (p.s2) {
+            // stride-2 conv: sub-tile = bw x bh output pixels of image b; input pixel of tap (dy,dx) is (2*yo+dy, 2*xo+dx)
+            // in padded coordinates, fetched by one 4-D TMA box with traversal stride 2 in x and y
+            const int dy = p.ntaps == 9 ? grp / 3 : 1, dx = p.ntaps == 9 ? grp % 3 : 1;
+            for (int mt = 0; mt < g.MT; ++mt) {
+                const int pi = m_t * g.MT + mt;
+                const int b = pi / per_img;
+                const int rem = pi - b * per_img;
+                const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
+                tma_load_4d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, 2 * tx * p.s2_bw + dx, 2 * ty * p.s2_bh + dy, b, fb);
+            }
+        } else {
+            int shift = 0;
+            if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
+            else if (p.ntaps == 4) shift = (grp - 2) * p.Wp;          // stem: row pairs yo-1 .. yo+2 (plan.py stem7x7s2)
+            for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
+        }
+    };
     // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; its results may
-    // only be touched after this wait.
+    // only be touched after `griddepcontrol.wait`.  Weights do not depend on the previous kernel: the producer arms the first
+    // pipeline stages and fetches their weight tiles BEFORE the wait, so only the activation tiles see the dependency.
+    const bool run = !(p.dbg & 64);
+    int pre = 0;                                          // pipeline steps whose weight tiles were fetched ahead of the wait
+    if (warp_idx == 0 && lane == 0 && run && g.pdl && g.prefetch_w && !(p.dbg & 32) && (int)blockIdx.x < g.total_tiles) {
+        const int steps_tile = o_cnt * p.kpt * i_cnt;
+        pre = steps_tile < stages ? steps_tile : stages;
+        const int n0 = ((int)blockIdx.x % g.n_tiles) * p.BN;
+        for (int j = 0; j < pre; ++j) {
+            const int in = j % i_cnt, kc = (j / i_cnt) % p.kpt, o = j / (i_cnt * p.kpt);
+            const uint32_t fb = smem_u32(&full_bar[j]);
+            mbar_expect_tx(fb, tx_bytes);
+            load_b(dx_inner ? o * 3 + in : o, kc, n0, (uint32_t)j, fb);
+        }
+    }
     if (g.pdl) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
 
-    if (p.dbg & 64) {
+    if (!run) {
         // DEBUG: launch skeleton only
     } else if (warp_idx == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
-            const uint32_t a_bytes = p.s2 ? (uint32_t)(p.s2_bw * p.s2_bh * BK * 2) : (uint32_t)(g.slab ? V3_SLAB_BYTES : A_STAGE_BYTES);
-            const uint32_t tx_bytes = (uint32_t)g.MT * a_bytes + (uint32_t)(taps_per_step * p.BN * BK * 2);
-            const int n_grp = g.slab ? 3 : p.ntaps;              // outer tap groups (slab: dy)
-            const bool dx_inner = (!g.slab && p.ntaps == 9);      // plain 9-tap order is (dy, k-block, dx) too
-            const int per_img = p.s2_tw * p.s2_th;
             uint32_t s = 0, ph = 0;
+            int step = 0;                                        // steps issued by this CTA (only compared against `pre`)
             for (int w = blockIdx.x; w < g.total_tiles; w += gridDim.x) {
                 if (p.dbg & 32) break;                           // DEBUG: no loads at all
                 const int n_t = w % g.n_tiles, m_t = w / g.n_tiles;
                 const int n0 = n_t * p.BN;
-                const int m0 = m_t * BMT;
-                const int o_cnt = dx_inner ? 3 : n_grp;          // outer loop: dy (9-tap plain) or tap group
-                const int i_cnt = dx_inner ? 3 : 1;              // inner loop: dx (9-tap plain)
                 for (int o = 0; o < o_cnt; ++o) {
                     for (int kc = 0; kc < p.kpt; ++kc) {
                         for (int in = 0; in < i_cnt; ++in) {
                             const int grp = dx_inner ? o * 3 + in : o;
-                            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                             const uint32_t fb = smem_u32(&full_bar[s]);
-                            mbar_expect_tx(fb, tx_bytes);
-                            const uint32_t a_dst = smem_base + s * g.stage_bytes;
-                            const uint32_t b_dst = a_dst + g.MT * g.a_sub_bytes;
-                            if (g.slab) {
-                                const int r0 = m0 + (grp - 1) * p.Wp - 1;
-                                for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, r0 + mt * BM, fb);
-                                for (int dx = 0; dx < 3; ++dx) tma_load_2d(b_dst + dx * g.b_bytes, &tmB, (grp * 3 + dx) * p.Kc + kc * BK, n0, fb);
-                            } else if (p.s2) {
-                                // stride-2 conv: sub-tile = bw x bh output pixels of image b; input pixel of tap (dy,dx) is (2*yo+dy, 2*xo+dx)
-                                // in padded coordinates, fetched by one 4-D TMA box with traversal stride 2 in x and y
-                                const int dy = p.ntaps == 9 ? grp / 3 : 1, dx = p.ntaps == 9 ? grp % 3 : 1;
-                                for (int mt = 0; mt < g.MT; ++mt) {
-                                    const int pi = m_t * g.MT + mt;
-                                    const int b = pi / per_img;
-                                    const int rem = pi - b * per_img;
-                                    const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
-                                    tma_load_4d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, 2 * tx * p.s2_bw + dx, 2 * ty * p.s2_bh + dy, b, fb);
-                                }
-                                tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
+                            if (step < pre) {
+                                load_a(grp, kc, m_t, s, fb);     // stage already armed, weights already in flight
                             } else {
-                                int shift = 0;
-                                if (p.ntaps == 9) shift = (grp / 3 - 1) * p.Wp + (grp % 3 - 1);
-                                else if (p.ntaps == 4) shift = (grp - 2) * p.Wp;          // stem: row pairs yo-1 .. yo+2 (plan.py stem7x7s2)
-                                for (int mt = 0; mt < g.MT; ++mt) tma_load_2d(a_dst + mt * g.a_sub_bytes, &tmA, kc * BK, m0 + shift + mt * BM, fb);
-                                tma_load_2d(b_dst, &tmB, grp * p.Kc + kc * BK, n0, fb);
+                                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                                mbar_expect_tx(fb, tx_bytes);
+                                load_a(grp, kc, m_t, s, fb);
+                                load_b(grp, kc, n0, s, fb);
                             }
+                            ++step;
                             if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                         }
                     }
@@ -242,18 +275,17 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     bool ok = row < p.M;
                     if (p.s2) {
                         const int pi = m_t * g.MT + mt;
-                        const int b = pi / per_img;
+                        const int b = fast_div(pi, g.fd_per_img);
                         const int rem = pi - b * per_img;
-                        const int ty = rem / p.s2_tw, tx = rem - ty * p.s2_tw;
-                        const int j = r / p.s2_bw, i = r - j * p.s2_bw;
+                        const int ty = fast_div(rem, g.fd_tw), tx = rem - ty * p.s2_tw;
+                        const int j = fast_div(r, g.fd_bw), i = r - j * p.s2_bw;
                         const int yo = ty * p.s2_bh + j, xo = tx * p.s2_bw + i;
                         ok = (pi < g.n_patches) && (r < p.s2_bw * p.s2_bh) && (yo < p.s2_Ho) && (xo < p.s2_Wo);
                         row = (b * (p.s2_Ho + 2) + yo + 1) * (p.s2_Wo + 2) + xo + 1;
                     } else if (p.mask_H > 0 && ok) {
                         const int Wp = p.mask_W + 2;
-                        const int img = (p.mask_H + 2) * Wp;
-                        const int pp = row % img;
-                        const int yy = pp / Wp;
+                        const int pp = row - fast_div(row, g.fd_img) * g.fd_img.d;
+                        const int yy = fast_div(pp, g.fd_wp);
                         const int xx = pp - yy * Wp;
                         ok = (yy >= 1) && (yy <= p.mask_H) && (xx >= 1) && (xx <= p.mask_W);
                     }
@@ -314,7 +346,7 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) silu4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int j = 0; j < 16; j += 2) silu2(f[j], f[j + 1]);
                         } else if (act == 2) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -441,6 +473,20 @@ static int v3_device_state(int* num_sms) {
     return 0;
 }
 
+static FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d < 1 ? 1 : d;
+    f.mul = 0; f.shr = 0;
+    if (f.d > 1) {
+        int lg = 0;
+        while ((1u << lg) < (uint32_t)f.d) ++lg;          // ceil(log2(d))
+        const int p = 31 + lg;
+        f.mul = (uint32_t)((((uint64_t)1 << p) + (uint64_t)f.d - 1) / (uint64_t)f.d);
+        f.shr = (uint32_t)(p - 32);
+    }
+    return f;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -481,7 +527,14 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     g->m_tiles = (p.M + BMT - 1) / BMT;
     g->total_tiles = g->n_tiles * g->m_tiles;
     g->n_patches = p.s2 ? p.M / BM : 0;
+    g->fd_img = make_fastdiv((p.mask_H + 2) * (p.mask_W + 2));
+    g->fd_wp = make_fastdiv(p.mask_W + 2);
+    g->fd_per_img = make_fastdiv(p.s2 ? p.s2_tw * p.s2_th : 1);
+    g->fd_tw = make_fastdiv(p.s2 ? p.s2_tw : 1);
+    g->fd_bw = make_fastdiv(p.s2 ? p.s2_bw : 1);
     g->pdl = 0;
+    static const int no_prefetch = env_int("ADAS_B200_NO_WPREFETCH", 0);
+    g->prefetch_w = no_prefetch ? 0 : 1;
     return 0;
 }
 

@@ -153,6 +153,26 @@ __device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3
 }
 
 
+// SiLU of two values with one reciprocal: 1/(1+t0) = (1+t1) / ((1+t0)(1+t1)).  Per element 1.5 SFU ops (ex2 + half a rcp) and 4.5
+// fp32 ops -- the 16-warp epilogue is bound by instruction issue (ncu, profiles/r02_*), and this form issues ~7 instructions per
+// element against ~10.5 for the four-value form.  Arguments are clamped at -40 so the product of two (1 + e^40) stays inside fp32
+// (SiLU(-40) = -1.7e-16 rounds to -0 in half precision either way).
+__device__ __forceinline__ void silu2(float& x0, float& x1) {
+    const float L = -1.4426950408889634f;
+    const float a0 = 1.0f + ex2_approx(fmaxf(x0, -40.f) * L);
+    const float a1 = 1.0f + ex2_approx(fmaxf(x1, -40.f) * L);
+    const float r = rcp_approx(a0 * a1);
+    x0 *= r * a1;
+    x1 *= r * a0;
+}
+
+// n / d for 0 <= n < 2^31 without a hardware divide (the epilogue computes two quotients per thread and sub-tile).
+struct FastDiv {
+    uint32_t mul, shr;
+    int d;
+};
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
+
 // ---- TMA stores (shared -> global), bulk async groups -----------------------------------------------------------------
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

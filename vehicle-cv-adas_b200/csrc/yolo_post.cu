@@ -11,6 +11,7 @@
 //                                                                  (view aliasing), scores/areas really swapped;
 //                                                                  emits dets[:,4][scores > 0.001] (duplicates possible)
 #include "common.h"
+#include <mutex>
 
 namespace adas {
 
@@ -188,7 +189,7 @@ struct NmsSmem {   // dynamic smem carve-up, cap entries each
 
 __global__ void __launch_bounds__(NMS_THREADS)
 yolo_compact_nms_kernel(const float* __restrict__ raw, int kind, int A, int nc, LetterboxGeom g, double nms_iou,
-                        int max_det, int cap, const int32_t* __restrict__ flags, const int32_t* __restrict__ cls,
+                        int max_det, int cap, int scap, double* __restrict__ work, const int32_t* __restrict__ flags, const int32_t* __restrict__ cls,
                         const float* __restrict__ conf, int32_t* __restrict__ n_cand, float* __restrict__ cand_box,
                         float* __restrict__ cand_conf, int32_t* __restrict__ cand_cls, float* __restrict__ out_box,
                         float* __restrict__ out_score, int32_t* __restrict__ out_cls, int32_t* __restrict__ out_idx,
@@ -234,8 +235,12 @@ yolo_compact_nms_kernel(const float* __restrict__ raw, int kind, int A, int nc, 
     const float ratiow = (float)((double)g.src_w / (double)g.new_w);
     const float padw = (float)g.pad_w, padh = (float)g.pad_h;
 
-    double* X1 = nms_sm; double* Y1 = X1 + cap; double* X2 = Y1 + cap; double* Y2 = X2 + cap;
-    double* ID = Y2 + cap; double* SC = ID + cap; double* AR = SC + cap;
+    // NMS working set (7 doubles per candidate): shared memory while it fits (`scap` candidates), else this frame's slice of a
+    // global scratch sized for every anchor -- the reference has no candidate limit (yoloDetector.py:104-133 keeps them all)
+    double* base = (total <= scap) ? nms_sm : work + (size_t)b * cap * 7;
+    const int cs = (total <= scap) ? scap : cap;
+    double* X1 = base; double* Y1 = X1 + cs; double* X2 = Y1 + cs; double* Y2 = X2 + cs;
+    double* ID = Y2 + cs; double* SC = ID + cs; double* AR = SC + cs;
 
     for (int a = a0; a < a1; ++a) {
         if (!fl[a]) continue;
@@ -340,13 +345,20 @@ int launch_yolo_post(const float* raw, int kind, int B, int A, int nc, const Let
     yolo_select_kernel<<<blocks, 128, 0, st>>>(raw, kind, B, A, nc, box_score, w.flags, w.cls, w.conf);
     count_launch();
     ADAS_CUDA(cudaGetLastError());
-    const int smem = w.cap * 7 * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        ADAS_CUDA(cudaFuncSetAttribute(yolo_compact_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+    const int scap = w.cap < 2048 ? w.cap : 2048;            // candidates whose working set lives in shared memory (112 KiB)
+    const int smem = scap * 7 * (int)sizeof(double);
+    {   // the >48 KiB opt-in is a per-device attribute: set it once per device (advisor finding, r01)
+        static std::mutex mu;
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        ADAS_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            ADAS_CUDA(cudaFuncSetAttribute(yolo_compact_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[dev] = true;
+        }
     }
-    yolo_compact_nms_kernel<<<B, NMS_THREADS, smem, st>>>(raw, kind, A, nc, g, nms_iou, max_det, w.cap, w.flags, w.cls, w.conf,
+    yolo_compact_nms_kernel<<<B, NMS_THREADS, smem, st>>>(raw, kind, A, nc, g, nms_iou, max_det, w.cap, scap, w.nms_work, w.flags, w.cls, w.conf,
                                                           w.n_cand, w.cand_box, w.cand_conf, w.cand_cls, w.out_box,
                                                           w.out_score, w.out_cls, w.out_idx, w.out_count);
     count_launch();

@@ -25,17 +25,17 @@ from .ObjectTracker import BYTETracker
 
 
 class StepResult:
-    __slots__ = ("boxes", "scores", "class_ids", "counts", "lane_pts", "lane_npts", "lane_status", "tracks")
+    __slots__ = ("boxes", "scores", "class_ids", "cand_index", "counts", "n_candidates", "lane_pts", "lane_npts", "lane_status", "tracks")
 
     def __init__(self, y, u):
-        self.boxes, self.scores, self.class_ids, _, self.counts, _ = y
+        self.boxes, self.scores, self.class_ids, self.cand_index, self.counts, self.n_candidates = y
         self.lane_pts, self.lane_npts, self.lane_status, _ = u
         self.tracks: Optional[List[list]] = None
 
 
 class AdasPipeline:
     def __init__(self, yolo_plan: str, ufld_plan: str, device: int = 0, batch: int = 8, box_score: float = 0.4, box_nms_iou: float = 0.45,
-                 max_det: int = 300, class_names: Optional[List[str]] = None, depth: int = 3, sets: int = 2):
+                 max_det: int = 1024, class_names: Optional[List[str]] = None, depth: int = 3, sets: int = 2):
         self.batch, self.box_score, self.box_nms_iou, self.max_det = batch, box_score, box_nms_iou, max_det
         # `sets` independent (object engine, lane engine) pairs: consecutive batches alternate between them so the next batch's
         # kernels are already queued on the device (own streams, own activation buffers) while the previous batch drains --

@@ -207,7 +207,7 @@ def run_b200(args):
         for b, tr in enumerate(r.tracks or []):
             n = min(len(tr), MAX_DET)
             if n:
-                rec[b, :n, 6] = [t["track_id"] for t in tr[:n]]
+                rec[b, :n, 6] = tr["track_id"][:n]
         with torch.cuda.stream(gather_stream):
             hist[slot].copy_(rec_host[k], non_blocking=True)
             rec_ev[k].record(gather_stream)

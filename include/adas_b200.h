@@ -174,7 +174,7 @@ int adas_associate(int device, int T, int D, const double* a_tlbr, const double*
 typedef struct adas_tracker adas_tracker;
 typedef struct adas_track {
     int32_t track_id, state /* 0 new 1 tracked 2 lost 3 removed */, is_activated, class_id;
-    int32_t start_frame, frame_id, tracklet_len, pad;
+    int32_t start_frame, frame_id, tracklet_len, pad /* BaseTrack._count when the record was written */;
     double score;
     double tlwh[4];      /* current box (Kalman state), top-left x, y, w, h */
     double mean[8];      /* Kalman mean (cx, cy, a, h, velocities) */
@@ -190,6 +190,11 @@ int adas_tracker_reset(adas_tracker* t);
  * writes up to max_out tracked tracks (tracked_stracks order) and their count */
 int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores,
                         const int32_t* class_ids, int max_out, adas_track* out, int* n_out);
+/* all frames of one pipeline step in one call (no interpreter work between frames): counts[n_frames] detections per frame,
+ * boxes / scores / class ids concatenated in frame order; out holds n_frames * max_out records, n_out[f] the tracked-track count
+ * of frame f (records beyond max_out are dropped from `out`, never from the tracker). */
+int adas_tracker_update_batch(adas_tracker* t, int n_frames, const int32_t* counts, const double* boxes_xyxy,
+                              const double* scores, const int32_t* class_ids, int max_out, adas_track* out, int32_t* n_out);
 int adas_tracker_get(adas_tracker* t, int which /* 0 tracked, 1 lost, 2 removed */, int max_out, adas_track* out, int* n_out);
 int adas_tracker_count(void);    /* BaseTrack._count */
 

@@ -367,8 +367,9 @@ def test_pipeline_overlapped_equals_synchronous():
         for i in range(ra.lane_pts.shape[0]):
             for l in range(4):
                 assert np.array_equal(ra.lane_pts[i, l, :ra.lane_npts[i, l]], rb.lane_pts[i, l, :rb.lane_npts[i, l]])
-        key = lambda t: (t["track_id"], t["location"], t["score"], t["class_id"], t["curr_frame_number"], t["is_activated"], t["count"])
-        assert [[key(t) for t in fr] for fr in ra.tracks] == [[key(t) for t in fr] for fr in rb.tracks]
+        assert len(ra.tracks) == len(rb.tracks)
+        for ta, tb in zip(ra.tracks, rb.tracks):                          # TRACK_DTYPE record arrays, one per frame
+            assert ta.tobytes() == tb.tobytes()
     assert dets > 0
 
 

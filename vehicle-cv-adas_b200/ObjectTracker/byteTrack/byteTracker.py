@@ -247,6 +247,36 @@ class BYTETracker(ObjectTrackBase):
         cnt = self._capi.NativeTracker.count()
         return [t.get_track_message(cnt) for t in self.tracked_stracks]
 
+    def update_batch(self, frames_dets, max_out: int = 256):
+        """All frames of a pipeline step in ONE library call (no interpreter work between frames).
+        frames_dets: sequence of (bboxes xyxy [n,4], scores [n], class_ids [n]) per frame, in time order.
+        Returns one TRACK_DTYPE record array per frame (the tracked_stracks of that frame); `messages(recs)` turns a record array into
+        the reference's track messages (strack.py:207-215).  `tracked_stracks` afterwards reflects the last frame."""
+        counts = np.fromiter((len(d[1]) for d in frames_dets), dtype=np.int32, count=len(frames_dets))
+        tot = int(counts.sum())
+        boxes = np.zeros((tot, 4), np.float64)
+        scores = np.zeros(tot, np.float64)
+        ids = np.zeros(tot, np.int32)
+        o = 0
+        for (bb, sc, cl), n in zip(frames_dets, counts):
+            if n:
+                boxes[o:o + n] = np.asarray(bb, dtype=np.float64).reshape(-1, 4)
+                scores[o:o + n] = np.asarray(sc, dtype=np.float64)
+                ids[o:o + n] = [self._cid(c) for c in (cl.tolist() if hasattr(cl, "tolist") else cl)]
+            o += n
+        recs = self._nt.update_batch(counts, boxes, scores, ids, max_out)
+        self.frame_id += len(frames_dets)
+        if recs:
+            self.tracked_stracks = [self._view(r, None) for r in recs[-1]]
+        return recs
+
+    def messages(self, recs):
+        """Track messages (STrack.get_track_message, strack.py:207-215) of one frame's record array."""
+        return [{"track_id": int(r["track_id"]), "count": int(r["pad"]), "is_activated": bool(r["is_activated"]), "state": int(r["state"]),
+                 "score": float(r["score"]), "start_frame_number": int(r["start_frame"]), "curr_frame_number": int(r["frame_id"]),
+                 "time_since_update": 0, "location": str((np.inf, np.inf)), "crops": [], "class_id": self._label_list[int(r["class_id"])]}
+                for r in recs]
+
     @property
     def lost_stracks(self):
         out = []

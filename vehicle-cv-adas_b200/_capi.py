@@ -24,7 +24,7 @@ SYMBOLS = [
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
-    "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_get", "adas_tracker_count",
+    "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_update_batch", "adas_tracker_get", "adas_tracker_count",
 ]
 
 
@@ -101,6 +101,21 @@ class NativeTracker:
         check(lib().adas_tracker_update(self._h, int(b.shape[0]), _p(b, C.c_double), _p(s, C.c_double), _p(c, C.c_int32), self.MAX_OUT,
                                         self._out.ctypes.data_as(C.c_void_p), C.byref(n)))
         return self._out[:min(n.value, self.MAX_OUT)].copy()
+
+    def update_batch(self, counts, boxes_xyxy, scores, class_ids, max_out: int = 256):
+        """All frames of a step in one library call -> list (per frame) of TRACK_DTYPE record arrays."""
+        cnt = as_c(counts, np.int32)
+        nf = int(cnt.shape[0])
+        b = as_c(np.asarray(boxes_xyxy, np.float64).reshape(-1, 4), np.float64)
+        s = as_c(scores, np.float64)
+        c = as_c(class_ids, np.int32)
+        out = np.zeros((nf, max_out), TRACK_DTYPE)
+        n_out = np.zeros(nf, np.int32)
+        check(lib().adas_tracker_update_batch(self._h, nf, _p(cnt, C.c_int32), _p(b, C.c_double), _p(s, C.c_double), _p(c, C.c_int32), int(max_out),
+                                              out.ctypes.data_as(C.c_void_p), _p(n_out, C.c_int32)))
+        if int(n_out.max(initial=0)) > max_out:          # rare: more live tracks than the caller-sized output rows; redo nothing, tell the caller
+            raise Exception(f"adas_tracker_update_batch: {int(n_out.max())} tracks exceed max_out {max_out}")
+        return [out[f, :int(n_out[f])] for f in range(nf)]
 
     def get(self, which: int) -> np.ndarray:
         n = C.c_int()

@@ -303,26 +303,31 @@ namespace adas {
 // Replaces the first Linear of the UFLDv2 head (exportLib/ultrafastLaneV2/model_culane.py:35-37, `cls` Sequential) at the batch
 // sizes the pipeline uses: out[b][n] = act(bias[n] + sum_k x[b][k] * W[n][k]).  At batch <= 32 the layer is a stream of the
 // weight matrix (FC1: 2048 x 4992 fp16 = 20 MB, L2-resident): the swap-AB tensor-core GEMM had 8 CTAs for it (47.8 us, 0.43 TB/s).
-// One warp owns FC_F output features and 8 batch rows; lanes stride over K in 16-byte chunks, fp32 accumulation, fixed xor-shuffle
-// reduction.  Every (b, n) value is computed by the same instruction sequence whatever the batch size (batch rows are independent
+// One CTA owns FC_F output features and 8 batch rows; its 8 warps split K, lanes stride over 16-byte chunks (8 independent weight
+// loads per lane per step), fp32 accumulation, fixed-order reduction (xor-shuffle over lanes, then warps in ascending order).  Every (b, n) value is computed by the same instruction sequence whatever the batch size (batch rows are independent
 // accumulators), so per-frame results do not depend on the batch.
-static constexpr int FC_F = 4;          // features per warp
-static constexpr int FC_WARPS = 8;
+static constexpr int FC_F = 8;          // output features per CTA
+static constexpr int FC_WARPS = 8;      // each warp owns one K slice of all FC_F features (many independent 16-byte loads in flight)
 
 __global__ void __launch_bounds__(32 * FC_WARPS)
 fc_stream_kernel(const __half* __restrict__ x, int x_ld, int batch, const __half* __restrict__ W, int K, int N, const float* __restrict__ bias,
                  int act, void* __restrict__ out, int out_ld, int out_f32) {
+    __shared__ float part[FC_WARPS][FC_F][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = (blockIdx.x * FC_WARPS + warp) * FC_F;
+    const int n0 = blockIdx.x * FC_F;
     const int b0 = blockIdx.y * 8;
-    if (n0 >= N) return;
+    const int nb = min(8, batch - b0);
+    // K slice of this warp, in 8-element (16-byte) chunks
+    const int chunks = K >> 3;
+    const int per = (chunks + FC_WARPS - 1) / FC_WARPS;
+    const int c0 = warp * per, c1 = min(chunks, c0 + per);
     float acc[FC_F][8];
 #pragma unroll
     for (int f = 0; f < FC_F; ++f)
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[f][b] = 0.f;
-    const int nb = min(8, batch - b0);
-    for (int k = lane * 8; k < K; k += 32 * 8) {
+    for (int c = c0 + lane; c < c1; c += 32) {
+        const int k = c << 3;
         uint4 w4[FC_F];
 #pragma unroll
         for (int f = 0; f < FC_F; ++f) {
@@ -352,29 +357,30 @@ fc_stream_kernel(const __half* __restrict__ x, int x_ld, int batch, const __half
             }
         }
     }
+    // fixed-order reduction: lanes (xor tree), then warps (ascending) -- the same sequence whatever the batch size
 #pragma unroll
     for (int f = 0; f < FC_F; ++f)
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
+        for (int b = 0; b < 8; ++b) {
+            float v = acc[f][b];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[f][b] += __shfl_xor_sync(0xffffffffu, acc[f][b], o);
-    if (lane == 0) {
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[warp][f][b] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < FC_F * 8) {
+        const int f = threadIdx.x >> 3, b = threadIdx.x & 7;
+        const int n = n0 + f;
+        if (n < N && b < nb) {
+            float v = 0.f;
 #pragma unroll
-        for (int f = 0; f < FC_F; ++f) {
-            const int n = n0 + f;
-            if (n >= N) break;
-            const float bv = bias ? bias[n] : 0.f;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (b < nb) {
-                    float v = acc[f][b] + bv;
-                    if (act == 1) v = v / (1.f + __expf(-v));
-                    else if (act == 2) v = fmaxf(v, 0.f);
-                    const size_t o = (size_t)(b0 + b) * out_ld + n;
-                    if (out_f32) reinterpret_cast<float*>(out)[o] = v;
-                    else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
-                }
-            }
+            for (int w = 0; w < FC_WARPS; ++w) v += part[w][f][b];
+            v += bias ? bias[n] : 0.f;
+            if (act == 1) v = v / (1.f + __expf(-v));
+            else if (act == 2) v = fmaxf(v, 0.f);
+            const size_t o = (size_t)(b0 + b) * out_ld + n;
+            if (out_f32) reinterpret_cast<float*>(out)[o] = v;
+            else reinterpret_cast<__half*>(out)[o] = __float2half_rn(v);
         }
     }
 }
@@ -382,7 +388,7 @@ fc_stream_kernel(const __half* __restrict__ x, int x_ld, int batch, const __half
 int launch_fc_stream(const __half* x, int x_ld, int batch, const __half* W, int K, int N, const float* bias, int act, void* out, int out_ld,
                      int out_f32, cudaStream_t st) {
     ADAS_CHECK(K % 8 == 0 && x_ld % 8 == 0, "fc_stream: K (%d) and the activation row stride (%d) must be multiples of 8", K, x_ld);
-    dim3 grid((N + FC_WARPS * FC_F - 1) / (FC_WARPS * FC_F), (batch + 7) / 8, 1);
+    dim3 grid((N + FC_F - 1) / FC_F, (batch + 7) / 8, 1);
     fc_stream_kernel<<<grid, 32 * FC_WARPS, 0, st>>>(x, x_ld, batch, W, K, N, bias, act, out, out_ld, out_f32);
     count_launch();
     ADAS_CUDA(cudaGetLastError());

@@ -345,8 +345,13 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 }
                         }
                         if (act == 1) {
+                            if (p.dbg & 128) {                      // DEBUG: four-value SiLU of the round-1 kernel (numerics A/B)
 #pragma unroll
-                            for (int j = 0; j < 16; j += 2) silu2(f[j], f[j + 1]);
+                                for (int j = 0; j < 16; j += 4) silu4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) silu2(f[j], f[j + 1]);
+                            }
                         } else if (act == 2) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);

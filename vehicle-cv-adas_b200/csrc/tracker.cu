@@ -3,9 +3,9 @@
 // Replaces the per-frame Python of ObjectTracker/byteTrack/byteTracker.py:62-185 (three association stages, births,
 // ageing, list maintenance), dtypes/strack.py (track records, class vote, conversions), dtypes/kalman_filter.py:55-226
 // (constant-velocity filter, float64) and utils.py:9-69 (joint / sub / duplicate removal).  The IoU cost matrices and
-// the exact assignment of every stage run on the device (iou_cost_kernel + lap_kernel, one launch pair and one
-// synchronisation per stage); the 8x8 float64 Kalman algebra and the list bookkeeping are sequential per stream and
-// stay on the host, now without interpreter overhead.
+// the exact assignment of all three stages of a frame run on the device in ONE launch (track.cu assoc3_kernel: one upload, one
+// launch, one download, one synchronisation per frame); the 8x8 float64 Kalman algebra and the list bookkeeping are sequential
+// per stream and stay on the host.  adas_tracker_update_batch takes all frames of a pipeline step in one call.
 #include "common.h"
 #include "../../include/adas_b200.h"
 #include <math.h>
@@ -21,6 +21,7 @@ int launch_lap(int problems, const double* cost, const int64_t* cost_off, const 
                const double* thresh, int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off, double* work_v,
                double* work_minv, int32_t* work_i, cudaStream_t st);
 int lap_max_cols();
+int launch_assoc3(const double* in, int32_t* out, double* cost, double* work_v, double* work_minv, int32_t* work_i, int32_t* lists, cudaStream_t st);
 
 enum { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
 static std::atomic<int> g_track_count{0};          // BaseTrack._count: process-global (base_track.py:12,33-36)
@@ -132,6 +133,10 @@ struct adas_tracker {
     int64_t* d_co = nullptr;
     std::vector<double> ha, hb, hs;
     std::vector<int32_t> hx, hy;
+    // fused three-stage association (one launch + one synchronisation per frame)
+    double* h3_in = nullptr; int32_t* h3_out = nullptr;      // pinned
+    double* d3_in = nullptr; int32_t* d3_out = nullptr; double* d3_cost = nullptr; int32_t* d3_lists = nullptr;
+    size_t cap3_in = 0, cap3_out = 0, cap3_cost = 0, cap3_lists = 0;
 };
 
 namespace adas {
@@ -153,39 +158,6 @@ static int ensure_scratch(adas_tracker* t, size_t nb, size_t nc) {
         ADAS_CUDA(cudaMalloc(&t->d_a, t->cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&t->d_b, t->cap_boxes * 32)); ADAS_CUDA(cudaMalloc(&t->d_s, t->cap_boxes * 8));
         ADAS_CUDA(cudaMalloc(&t->d_c, t->cap_cost * 8)); ADAS_CUDA(cudaMalloc(&t->d_x, t->cap_boxes * 4)); ADAS_CUDA(cudaMalloc(&t->d_y, t->cap_boxes * 4));
     }
-    return 0;
-}
-
-// one association stage on the device: cost = 1 - IoU (optionally fused with the detection scores), exact assignment
-static int associate(adas_tracker* t, const std::vector<TrackP>& trk, const std::vector<TrackP>& det, double thresh, bool fuse,
-                     std::vector<std::pair<int, int>>* matches, std::vector<int>* u_trk, std::vector<int>* u_det) {
-    matches->clear(); u_trk->clear(); u_det->clear();
-    const int T = (int)trk.size(), D = (int)det.size();
-    if (T == 0 || D == 0) {                        // matching.py:21-22
-        for (int i = 0; i < T; ++i) u_trk->push_back(i);
-        for (int j = 0; j < D; ++j) u_det->push_back(j);
-        return 0;
-    }
-    ADAS_CHECK(T + D <= lap_max_cols() && T <= lap_max_cols() / 2, "tracker: association too large (T=%d D=%d)", T, D);
-    if (ensure_scratch(t, (size_t)std::max(T, D), (size_t)T * D)) return 1;
-    t->ha.resize((size_t)T * 4); t->hb.resize((size_t)D * 4); t->hs.resize(D); t->hx.resize(T); t->hy.resize(D);
-    for (int i = 0; i < T; ++i) trk[i]->tlbr(&t->ha[(size_t)i * 4]);
-    for (int j = 0; j < D; ++j) { det[j]->tlbr(&t->hb[(size_t)j * 4]); t->hs[j] = det[j]->score; }
-    const int32_t meta[8] = {0, T, 0, D, T, D, 0, 0};
-    const int64_t co[2] = {0, (int64_t)T * D};
-    ADAS_CUDA(cudaMemcpyAsync(t->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, t->st));
-    ADAS_CUDA(cudaMemcpyAsync(t->d_co, co, sizeof(co), cudaMemcpyHostToDevice, t->st));
-    ADAS_CUDA(cudaMemcpyAsync(t->d_a, t->ha.data(), (size_t)T * 32, cudaMemcpyHostToDevice, t->st));
-    ADAS_CUDA(cudaMemcpyAsync(t->d_b, t->hb.data(), (size_t)D * 32, cudaMemcpyHostToDevice, t->st));
-    if (fuse) ADAS_CUDA(cudaMemcpyAsync(t->d_s, t->hs.data(), (size_t)D * 8, cudaMemcpyHostToDevice, t->st));
-    ADAS_CUDA(cudaMemcpyAsync(t->d_th, &thresh, 8, cudaMemcpyHostToDevice, t->st));
-    if (launch_iou_cost(1, t->d_a, t->d_meta, t->d_b, t->d_meta + 2, fuse ? t->d_s : nullptr, fuse ? 1 : 0, t->d_c, t->d_co, t->st)) return 1;
-    if (launch_lap(1, t->d_c, t->d_co, t->d_meta + 4, t->d_meta + 5, t->d_th, t->d_x, t->d_meta + 6, t->d_y, t->d_meta + 6, t->d_v, t->d_mv, t->d_wi, t->st)) return 1;
-    ADAS_CUDA(cudaMemcpyAsync(t->hx.data(), t->d_x, (size_t)T * 4, cudaMemcpyDeviceToHost, t->st));
-    ADAS_CUDA(cudaMemcpyAsync(t->hy.data(), t->d_y, (size_t)D * 4, cudaMemcpyDeviceToHost, t->st));
-    ADAS_CUDA(cudaStreamSynchronize(t->st));
-    for (int i = 0; i < T; ++i) { if (t->hx[i] >= 0) matches->push_back({i, t->hx[i]}); else u_trk->push_back(i); }
-    for (int j = 0; j < D; ++j) if (t->hy[j] < 0) u_det->push_back(j);
     return 0;
 }
 
@@ -230,9 +202,70 @@ static void fill_out(const Track& s, adas_track* o) {
     o->start_frame = s.start; o->frame_id = s.frame; o->tracklet_len = s.tracklet_len;
     s.tlwh(o->tlwh);
     if (s.has_kf) memcpy(o->mean, s.mean, 64); else memset(o->mean, 0, 64);
-    memcpy(o->det_tlbr, s.det_tlbr, 32); o->traj_frame = s.traj_frame; o->pad = 0; o->pad2 = 0;
+    memcpy(o->det_tlbr, s.det_tlbr, 32); o->traj_frame = s.traj_frame; o->pad2 = 0;
+    o->pad = g_track_count.load();          // BaseTrack._count when this record was written (the "count" of get_track_message)
 }
 
+}  // namespace adas
+
+namespace adas {
+// scratch of the fused association, sized for this frame (called before any tracker state is touched)
+static int assoc3_prepare(adas_tracker* t, int P, int U, int D, int D2) {
+    if (ensure_scratch(t, 1, 1)) return 1;
+    const size_t mr = (size_t)std::max(P, U), mc = (size_t)std::max(D, D2);
+    const size_t n_in = 5 + (size_t)P * 5 + (size_t)U * 4 + (size_t)D * 5 + (size_t)D2 * 4, n_out = (size_t)2 * P + U + D + 4;
+    const size_t n_cost = mr * mc + (size_t)D * 5 + (size_t)P * 4 + 8, n_lists = (size_t)P + D + mr + mc + 8;
+    if (n_in > t->cap3_in) {
+        if (t->h3_in) cudaFreeHost(t->h3_in);
+        cudaFree(t->d3_in);
+        t->cap3_in = std::max<size_t>(4096, n_in * 2);
+        ADAS_CUDA(cudaHostAlloc(&t->h3_in, t->cap3_in * 8, cudaHostAllocDefault));
+        ADAS_CUDA(cudaMalloc(&t->d3_in, t->cap3_in * 8));
+    }
+    if (n_out > t->cap3_out) {
+        if (t->h3_out) cudaFreeHost(t->h3_out);
+        cudaFree(t->d3_out);
+        t->cap3_out = std::max<size_t>(4096, n_out * 2);
+        ADAS_CUDA(cudaHostAlloc(&t->h3_out, t->cap3_out * 4, cudaHostAllocDefault));
+        ADAS_CUDA(cudaMalloc(&t->d3_out, t->cap3_out * 4));
+    }
+    if (n_cost > t->cap3_cost) { cudaFree(t->d3_cost); t->cap3_cost = std::max<size_t>(65536, n_cost * 2); ADAS_CUDA(cudaMalloc(&t->d3_cost, t->cap3_cost * 8)); }
+    if (n_lists > t->cap3_lists) { cudaFree(t->d3_lists); t->cap3_lists = std::max<size_t>(4096, n_lists * 2); ADAS_CUDA(cudaMalloc(&t->d3_lists, t->cap3_lists * 4)); }
+    return 0;
+}
+
+// the three association stages of one frame: one upload, one launch (track.cu assoc3_kernel), one download, one synchronisation
+static int assoc3_run(adas_tracker* t, const std::vector<TrackP>& pool, const std::vector<TrackP>& unconf, const std::vector<TrackP>& dets,
+                      const std::vector<TrackP>& dets2, bool need_dev, std::vector<int32_t>* m1, std::vector<int32_t>* m2, std::vector<int32_t>* m3,
+                      std::vector<int32_t>* free3) {
+    const int P = (int)pool.size(), U = (int)unconf.size(), D = (int)dets.size(), D2 = (int)dets2.size();
+    m1->assign(P, -1); m2->assign(P, -2); m3->assign(U, -1); free3->assign(D, 1);
+    if (!need_dev) {
+        // nothing to match against (matching.py:21-22): every Tracked pool row goes through stage 2 unmatched, every detection stays free
+        for (int i = 0; i < P; ++i) if (pool[i]->state == ST_TRACKED) (*m2)[i] = -1;
+        return 0;
+    }
+    double* h = t->h3_in;
+    h[0] = P; h[1] = U; h[2] = D; h[3] = D2; h[4] = t->match_thresh;
+    double* q = h + 5;
+    for (int i = 0; i < P; ++i, q += 4) pool[i]->tlbr(q);
+    for (int i = 0; i < P; ++i) *q++ = pool[i]->state == ST_TRACKED ? 1.0 : 0.0;
+    for (int i = 0; i < U; ++i, q += 4) unconf[i]->tlbr(q);
+    for (int j = 0; j < D; ++j, q += 4) dets[j]->tlbr(q);
+    for (int j = 0; j < D; ++j) *q++ = dets[j]->score;
+    for (int j = 0; j < D2; ++j, q += 4) dets2[j]->tlbr(q);
+    const size_t n_in = (size_t)(q - h), n_out = (size_t)2 * P + U + D;
+    ADAS_CUDA(cudaMemcpyAsync(t->d3_in, h, n_in * 8, cudaMemcpyHostToDevice, t->st));
+    if (launch_assoc3(t->d3_in, t->d3_out, t->d3_cost, t->d_v, t->d_mv, t->d_wi, t->d3_lists, t->st)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(t->h3_out, t->d3_out, n_out * 4, cudaMemcpyDeviceToHost, t->st));
+    ADAS_CUDA(cudaStreamSynchronize(t->st));
+    const int32_t* o = t->h3_out;
+    for (int i = 0; i < P; ++i) (*m1)[i] = o[i];
+    for (int i = 0; i < P; ++i) (*m2)[i] = o[P + i];
+    for (int k = 0; k < U; ++k) (*m3)[k] = o[2 * P + k];
+    for (int j = 0; j < D; ++j) (*free3)[j] = o[2 * P + U + j];
+    return 0;
+}
 }  // namespace adas
 
 extern "C" {
@@ -251,6 +284,9 @@ int adas_tracker_destroy(adas_tracker* t) {
     cudaSetDevice(t->device);
     cudaFree(t->d_a); cudaFree(t->d_b); cudaFree(t->d_s); cudaFree(t->d_c); cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_th); cudaFree(t->d_v);
     cudaFree(t->d_mv); cudaFree(t->d_wi); cudaFree(t->d_meta); cudaFree(t->d_co);
+    if (t->h3_in) cudaFreeHost(t->h3_in);
+    if (t->h3_out) cudaFreeHost(t->h3_out);
+    cudaFree(t->d3_in); cudaFree(t->d3_out); cudaFree(t->d3_cost); cudaFree(t->d3_lists);
     if (t->st) cudaStreamDestroy(t->st);
     delete t;
     return 0;
@@ -262,11 +298,8 @@ int adas_tracker_reset(adas_tracker* t) {          // BYTETracker.reset, byteTra
     return 0;
 }
 
-int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores, const int32_t* class_ids, int max_out,
-                        adas_track* out, int* n_out) {
-    ADAS_CHECK(t != nullptr && n >= 0, "adas_tracker_update: bad arguments");
-    ADAS_CUDA(cudaSetDevice(t->device));
-    t->frame_id += 1;
+static int update_one(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores, const int32_t* class_ids, int max_out,
+                      adas_track* out, int* n_out) {
     std::vector<TrackP> activated, refind, lost_now, removed_now, dets, dets2;
     for (int i = 0; i < n; ++i) {
         const double s = scores[i];
@@ -281,28 +314,28 @@ int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const 
     std::vector<TrackP> unconfirmed, confirmed;
     for (auto& x : t->tracked) (x->activated ? confirmed : unconfirmed).push_back(x);
     std::vector<TrackP> pool = joint(confirmed, t->lost);
+    // sizes are validated BEFORE any state is touched: a failed frame leaves the tracker exactly as it was (advisor finding, r01)
+    const int P = (int)pool.size(), U = (int)unconfirmed.size(), D = (int)dets.size(), D2 = (int)dets2.size();
+    ADAS_CHECK(P + D <= lap_max_cols() && P + D2 <= lap_max_cols() && U + D <= lap_max_cols() && P <= lap_max_cols() / 2 && U <= lap_max_cols() / 2,
+               "tracker: association too large (pool %d, unconfirmed %d, detections %d + %d)", P, U, D, D2);
+    std::vector<int32_t> m1, m2, m3, free3;
+    const bool need_dev = (P > 0 || U > 0) && (D > 0 || D2 > 0);
+    if (need_dev && assoc3_prepare(t, P, U, D, D2)) return 1;
+    t->frame_id += 1;
     for (auto& x : pool) kf_predict(*x);
-    std::vector<std::pair<int, int>> m;
-    std::vector<int> ut, ud;
+    if (assoc3_run(t, pool, unconfirmed, dets, dets2, need_dev, &m1, &m2, &m3, &free3)) { t->frame_id -= 1; return 1; }
     // stage 1: confirmed + lost vs high-score detections, fused cost
-    if (associate(t, pool, dets, t->match_thresh, true, &m, &ut, &ud)) return 1;
-    for (auto& pr : m) hit(t, *pool[pr.first], *dets[pr.second], &activated, &refind, pool[pr.first]);
-    // stage 2: still-tracked leftovers vs low-score detections, plain IoU
-    std::vector<TrackP> rem;
-    for (int i : ut) if (pool[i]->state == ST_TRACKED) rem.push_back(pool[i]);
-    std::vector<int> ut2, ud2;
-    if (associate(t, rem, dets2, 0.5, false, &m, &ut2, &ud2)) return 1;
-    for (auto& pr : m) hit(t, *rem[pr.first], *dets2[pr.second], &activated, &refind, rem[pr.first]);
-    for (int i : ut2) if (rem[i]->state != ST_LOST) { rem[i]->state = ST_LOST; lost_now.push_back(rem[i]); }
+    for (int i = 0; i < P; ++i) if (m1[i] >= 0) hit(t, *pool[i], *dets[m1[i]], &activated, &refind, pool[i]);
+    // stage 2: still-tracked leftovers vs low-score detections, plain IoU (m2 == -2: the row was not part of stage 2)
+    for (int i = 0; i < P; ++i) if (m2[i] >= 0) hit(t, *pool[i], *dets2[m2[i]], &activated, &refind, pool[i]);
+    for (int i = 0; i < P; ++i) if (m2[i] == -1 && pool[i]->state != ST_LOST) { pool[i]->state = ST_LOST; lost_now.push_back(pool[i]); }
     // stage 3: unconfirmed vs leftover high detections, fused cost
-    std::vector<TrackP> left;
-    for (int j : ud) left.push_back(dets[j]);
-    std::vector<int> uu, ud3;
-    if (associate(t, unconfirmed, left, 0.7, true, &m, &uu, &ud3)) return 1;
-    for (auto& pr : m) hit(t, *unconfirmed[pr.first], *left[pr.second], &activated, &activated, unconfirmed[pr.first]);
-    for (int i : uu) { unconfirmed[i]->state = ST_REMOVED; removed_now.push_back(unconfirmed[i]); }
+    for (int k = 0; k < U; ++k) if (m3[k] >= 0) hit(t, *unconfirmed[k], *dets[m3[k]], &activated, &activated, unconfirmed[k]);
+    for (int k = 0; k < U; ++k) if (m3[k] < 0) { unconfirmed[k]->state = ST_REMOVED; removed_now.push_back(unconfirmed[k]); }
     // births
-    for (int j : ud3) {
+    std::vector<TrackP>& left = dets;
+    for (int j = 0; j < D; ++j) {
+        if (!free3[j]) continue;
         Track& d = *left[j];
         if (d.score < t->det_thresh) continue;
         d.id = g_track_count.fetch_add(1) + 1;
@@ -342,6 +375,27 @@ int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const 
     int k = 0;
     for (auto& x : t->tracked) { if (out && k < max_out) fill_out(*x, &out[k]); ++k; }
     if (n_out) *n_out = k;
+    return 0;
+}
+
+int adas_tracker_update(adas_tracker* t, int n, const double* boxes_xyxy, const double* scores, const int32_t* class_ids, int max_out,
+                        adas_track* out, int* n_out) {
+    ADAS_CHECK(t != nullptr && n >= 0, "adas_tracker_update: bad arguments");
+    ADAS_CUDA(cudaSetDevice(t->device));
+    return update_one(t, n, boxes_xyxy, scores, class_ids, max_out, out, n_out);
+}
+
+int adas_tracker_update_batch(adas_tracker* t, int n_frames, const int32_t* counts, const double* boxes_xyxy, const double* scores,
+                              const int32_t* class_ids, int max_out, adas_track* out, int32_t* n_out) {
+    ADAS_CHECK(t != nullptr && n_frames >= 0 && counts != nullptr && n_out != nullptr, "adas_tracker_update_batch: bad arguments");
+    ADAS_CUDA(cudaSetDevice(t->device));
+    size_t off = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        int k = 0;
+        if (update_one(t, counts[f], boxes_xyxy + off * 4, scores + off, class_ids + off, max_out, out ? out + (size_t)f * max_out : nullptr, &k)) return 1;
+        n_out[f] = k;
+        off += (size_t)counts[f];
+    }
     return 0;
 }
 

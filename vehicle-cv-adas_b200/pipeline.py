@@ -78,17 +78,19 @@ class AdasPipeline:
         return self._pool.submit(self._detect_both, frames, on_device, shape, k)
 
     def _track(self, r: StepResult) -> None:
+        """ByteTrack for the frames of one batch, in time order, in ONE library call (adas_tracker_update_batch): r.tracks[i] is the
+        TRACK_DTYPE record array of frame i (`self.tracker.messages(r.tracks[i])` gives the reference's track messages)."""
         import time
         t0 = time.perf_counter()
-        out = []
+        dets = []
         for b in range(len(r.counts)):
             n = int(r.counts[b])
             bx = r.boxes[b, :n]
             # demo.py:272-275 feeds RectInfo.tolist("xyxy") -> ints, and the label as class id
             xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(int) if n else np.zeros((0, 4), int)
             ids = r.class_ids[b, :n] if self.class_names is None else [self.class_names[c] for c in r.class_ids[b, :n]]
-            out.append(self.tracker.update(xyxy, r.scores[b, :n], ids, None))
-        r.tracks = out
+            dets.append((xyxy, r.scores[b, :n], ids))
+        r.tracks = self.tracker.update_batch(dets)
         self.track_seconds = getattr(self, "track_seconds", 0.0) + (time.perf_counter() - t0)
         self.track_batches = getattr(self, "track_batches", 0) + 1
 

@@ -63,8 +63,8 @@ def build_plans(seed: int = 0):
     os.makedirs(CACHE, exist_ok=True)
     out = {}
     for kind, builder, kw in (("yolov8", plan.build_yolov8, dict(scale="l")), ("ufldv2", plan.build_ufldv2, dict(backbone="34"))):
-        path = os.path.join(CACHE, f"bench_{kind}_s{seed}.b200w")
-        W = plan.synth_weights(kind, seed, variant=kw.get("scale", kw.get("backbone")))
+        path = os.path.join(CACHE, f"bench_{kind}_s{seed}_workload.b200w")
+        W = plan.synth_weights(kind, seed, variant=kw.get("scale", kw.get("backbone")), workload=True)
         pb = builder(W, **kw)
         if not os.path.isfile(path):
             pb.write(path + f".{os.getpid()}.tmp")
@@ -181,42 +181,47 @@ def run_b200(args):
         hp[i] = np.roll(stream[(i % 4) * B:(i % 4 + 1) * B], shift=3 * i, axis=2)
     dev_pool = host_pool.to(f"cuda:{local}")
     torch.cuda.synchronize()
-    # BASELINE configs[4] "NCCL gather of boxes": every batch's detection/track records ([B, 300, 7] fp32) go pinned staging
-    # ring -> device history on a side stream; ONE NCCL all_gather of the history closes each run of steps, inside the timed
-    # region (a per-step all_gather was measured at 0.5 ms per step on 2 GPUs -- 13 % -- for 67 KB of payload).
-    HMAX = max(K, Wm + 2) + 2
-    REC = 4
+    # BASELINE configs[4] "NCCL gather of boxes": EVERY batch's detection / track records ([B, 300, 7] fp32, 67 KB) are all-gathered
+    # across the ranks inside the timed region: one library call per step (adas_comm_all_gather) stages the block, uploads it and runs
+    # ncclAllGather on the library's private stream with its own communicator -- no torch.distributed and no host synchronisation in
+    # the loop (round 1 exchanged once per run of steps because the Python-issued per-step collective cost 0.5 ms per step).
     multi = world > 1 and os.environ.get("ADAS_B200_NO_GATHER") != "1"
-    hist = torch.zeros((HMAX, B, MAX_DET, 7), dtype=torch.float32, device=f"cuda:{local}") if multi else None
-    hist_all = torch.zeros((world * HMAX, B, MAX_DET, 7), dtype=torch.float32, device=f"cuda:{local}") if multi else None
-    rec_host = [torch.zeros((B, MAX_DET, 7), dtype=torch.float32).pin_memory() for _ in range(REC)] if multi else []
-    rec_ev = [torch.cuda.Event() for _ in range(REC)] if multi else []
-    gather_stream = torch.cuda.Stream() if multi else None
+    comm = None
+    rec = np.zeros((B, MAX_DET, 7), np.float32) if multi else None
+    if multi:
+        from adas_b200 import _capi as _c
+        idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(_c.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)                      # start-up only: hand rank 0's NCCL id to the other ranks
+        sys.stdout.flush()
+        saved_fd2 = os.dup(1)
+        os.dup2(2, 1)                               # a new communicator may print the NCCL banner on stdout
+        try:
+            comm = _c.Comm(local, rank, world, bytes(idt.cpu().numpy().tobytes()), rec.nbytes)
+            comm.all_gather(rec)
+            comm.sync()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd2, 1)
+            os.close(saved_fd2)
     gather_n = [0]
 
     def gather(r):
         if not multi or r is None:
             return
-        k = gather_n[0] % REC
-        slot = gather_n[0] % HMAX
         gather_n[0] += 1
-        rec_ev[k].synchronize()                 # the copy that last used this staging buffer is long done
-        rec = rec_host[k].numpy()
         rec[..., :4], rec[..., 4], rec[..., 5] = r.boxes, r.scores, r.class_ids
         rec[..., 6] = 0
         for b, tr in enumerate(r.tracks or []):
             n = min(len(tr), MAX_DET)
             if n:
                 rec[b, :n, 6] = tr["track_id"][:n]
-        with torch.cuda.stream(gather_stream):
-            hist[slot].copy_(rec_host[k], non_blocking=True)
-            rec_ev[k].record(gather_stream)
+        comm.all_gather(rec)                        # asynchronous: returns as soon as the block is staged and the collective is enqueued
 
     def final_gather():
-        if not multi:
-            return
-        with torch.cuda.stream(gather_stream):
-            dist.all_gather_into_tensor(hist_all, hist)
+        if multi:
+            comm.sync()                             # every step's gather has completed before the timed region closes
 
     def barrier():
         torch.cuda.synchronize()
@@ -321,7 +326,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "YOLOv8l 640x640 + UFLDv2-CULane-ResNet34 320x1600 + ByteTrack, 1280x720 synthetic stream per GPU, "
                                    f"batch {B} frames per step (BASELINE configs[3]; configs[4] when n_gpus=8)",
-                       "global_batch": world * B, "parallelism": f"dp{world} (one stream per GPU; detection/track records of every batch NCCL all_gathered once per run of steps, inside the timed region)",
+                       "global_batch": world * B, "parallelism": f"dp{world} (one stream per GPU; the detection/track records of EVERY batch are NCCL all-gathered per step, inside the timed region, by the library's own communicator on a private stream)",
                        "weights": "seeded synthetic (He-normal, BN folded), fp16 operands, fp32 accumulate",
                        "l2": f"inputs rotate through a {pool_batches}-batch pool ({pool_batches * B * FRAME_H * FRAME_W * 3 / 1e6:.0f} MB > 126 MB L2)"},
             "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_H * FRAME_W * 3,
@@ -331,8 +336,9 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "host_tracker_ms_per_step": round(1e3 * getattr(pipe, "track_seconds", 0.0) / max(1, getattr(pipe, "track_batches", 1)), 3),
             "tracks_alive": len(pipe.tracker.tracked_stracks),
+            "gather": ({"per_step": True, "nccl_ranks": comm.info()[0], "all_gathers": comm.info()[1], "bytes_per_rank_per_step": int(rec.nbytes)} if comm is not None else None),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_v2_kernel (tcgen05 implicit-GEMM conv/FC, persistent)", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_v3_kernel (tcgen05 implicit-GEMM conv/FC, persistent, staged TMA-store epilogue)", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; GEMM launches timed alone, of measured)" if peaks else "fallback 1590 (of fallback)",
                          "launches_per_step": n_y + n_u, "avg_launch_us": round(1e3 * (ms_y + ms_u) / (n_y + n_u), 2),

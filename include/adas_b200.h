@@ -221,9 +221,20 @@ int adas_engine_num_steps(adas_engine* e, int batch, int* n);
 int adas_engine_time_step(adas_engine* e, int batch, int step, int iters, float* ms_per_iter, int* op_type, char* desc, int desc_cap);
 
 /* ---- optional multi-GPU gather -------------------------------------------------------------
- * (no reference counterpart: the reference is single-GPU)  The gather of
- * fixed-size detection records across ranks is done with torch.distributed (NCCL) in the
- * Python host layer; the library only needs to expose its stream for ordering. */
+ * (no reference counterpart: the reference is single-GPU; BASELINE configs[4] asks for an NCCL gather of boxes.)
+ * One communicator per process (one process per GPU): rank 0 makes the id with adas_comm_unique_id and hands its 128 bytes to the
+ * other ranks by any means (bench.py: torch.distributed broadcast at start-up); adas_comm_create joins (ncclCommInitRank) and owns a
+ * private stream.  adas_comm_all_gather takes this rank's record block of one batch (host memory, bytes_per_rank bytes), returns
+ * immediately and runs upload + ncclAllGather on that stream; adas_comm_sync waits for everything enqueued so far; adas_comm_read
+ * copies the last gathered [world, bytes_per_rank] block to the host.  NCCL is bound with dlopen at the first call. */
+typedef struct adas_comm adas_comm;
+int adas_comm_unique_id(uint8_t id[128]);
+int adas_comm_create(int device, int rank, int world, const uint8_t id[128], int64_t bytes_per_rank, adas_comm** out);
+int adas_comm_destroy(adas_comm* c);
+int adas_comm_all_gather(adas_comm* c, const void* host_src);
+int adas_comm_sync(adas_comm* c);
+int adas_comm_read(adas_comm* c, void* host_dst);
+int adas_comm_info(adas_comm* c, int* nranks, int64_t* gathers);
 int adas_engine_stream(const adas_engine* e, void** cuda_stream);
 
 #ifdef __cplusplus

@@ -269,3 +269,19 @@ def test_association_kernels(golden_dir):
         mine = c[np.nonzero(x >= 0)[0], x[x >= 0]].sum() + 0.4 * ((x < 0).sum() + (y < 0).sum())
         assert abs(mine - tot) < 1e-9
         assert np.array_equal(x, xo)
+
+
+def test_comm_single_rank_gather():
+    """adas_comm_*: the C-driven NCCL gather (own communicator, private stream) with world size 1 -- every call is asynchronous, the
+    staging ring is reused, the last block wins.  The 2 / 8 rank path is exercised by `bench.py --gpus N` (SCALE runs)."""
+    rec = np.arange(8 * 300 * 7, dtype=np.float32).reshape(8, 300, 7)
+    c = _capi.Comm(0, 0, 1, _capi.Comm.unique_id(), rec.nbytes)
+    for i in range(11):                      # more calls than ring slots
+        rec[0, 0, 0] = float(i)
+        c.all_gather(rec)
+    c.sync()
+    out = c.read()
+    assert out.shape == (1, rec.size)
+    assert out[0, 0] == 10.0 and np.array_equal(out[0, 1:], rec.ravel()[1:])
+    assert c.info() == (1, 11)
+    c.close()

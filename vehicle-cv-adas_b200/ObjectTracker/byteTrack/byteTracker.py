@@ -270,6 +270,24 @@ class BYTETracker(ObjectTrackBase):
             self.tracked_stracks = [self._view(r, None) for r in recs[-1]]
         return recs
 
+    def update_batch_arrays(self, counts, xyxy, scores, class_ids, max_out: int = 256):
+        """update_batch on already concatenated arrays (the pipeline's hot path): counts [F] int, xyxy [sum, 4], scores [sum],
+        class_ids [sum] integer labels.  Labels are mapped to the tracker's class slots in first-seen order like `update` does."""
+        cl = np.asarray(class_ids)
+        if cl.size:
+            uniq, first = np.unique(cl, return_index=True)
+            for u in uniq[np.argsort(first)].tolist():            # register unseen labels in order of first appearance
+                self._cid(u)
+            lut = np.array([self._labels[u] for u in uniq.tolist()], np.int32)
+            ids = lut[np.searchsorted(uniq, cl)]
+        else:
+            ids = np.zeros(0, np.int32)
+        recs = self._nt.update_batch(counts, xyxy, scores, ids, max_out)
+        self.frame_id += len(counts)
+        if recs:
+            self.tracked_stracks = [self._view(r, None) for r in recs[-1]]
+        return recs
+
     def messages(self, recs):
         """Track messages (STrack.get_track_message, strack.py:207-215) of one frame's record array."""
         return [{"track_id": int(r["track_id"]), "count": int(r["pad"]), "is_activated": bool(r["is_activated"]), "state": int(r["state"]),

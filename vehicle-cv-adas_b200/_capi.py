@@ -24,6 +24,7 @@ SYMBOLS = [
     "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
+    "adas_comm_unique_id", "adas_comm_create", "adas_comm_destroy", "adas_comm_all_gather", "adas_comm_sync", "adas_comm_read", "adas_comm_info",
     "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_update_batch", "adas_tracker_get", "adas_tracker_count",
 ]
 
@@ -388,3 +389,41 @@ def associate(a_tlbr, b_tlbr, det_scores, thresh: float, device: int = 0, want_c
     check(lib().adas_associate(device, T, D, _p(a, C.c_double), _p(b, C.c_double), _p(sc, C.c_double), 1 if fuse else 0, C.c_double(thresh),
                                _p(x, C.c_int32), _p(y, C.c_int32), _p(cost, C.c_double) if want_cost else None))
     return x[:T], y[:D], cost
+
+
+class Comm:
+    """NCCL gather of fixed-size per-batch record blocks, driven from C on a private stream (include/adas_b200.h, adas_comm_*)."""
+
+    def __init__(self, device: int, rank: int, world: int, unique_id: bytes, bytes_per_rank: int):
+        self._h = C.c_void_p()
+        idb = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().adas_comm_create(int(device), int(rank), int(world), idb, C.c_int64(bytes_per_rank), C.byref(self._h)))
+        self.world, self.bytes = world, bytes_per_rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        idb = (C.c_uint8 * 128)()
+        check(lib().adas_comm_unique_id(idb))
+        return bytes(idb)
+
+    def all_gather(self, rec: np.ndarray) -> None:
+        assert rec.nbytes == self.bytes and rec.flags["C_CONTIGUOUS"]
+        check(lib().adas_comm_all_gather(self._h, rec.ctypes.data_as(C.c_void_p)))
+
+    def sync(self) -> None:
+        check(lib().adas_comm_sync(self._h))
+
+    def read(self, dtype=np.float32) -> np.ndarray:
+        out = np.empty(self.world * self.bytes // np.dtype(dtype).itemsize, dtype)
+        check(lib().adas_comm_read(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(self.world, -1)
+
+    def info(self):
+        n, g = C.c_int(), C.c_int64()
+        check(lib().adas_comm_info(self._h, C.byref(n), C.byref(g)))
+        return int(n.value), int(g.value)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().adas_comm_destroy(self._h)
+            self._h = C.c_void_p()

@@ -35,7 +35,7 @@ class StepResult:
 
 class AdasPipeline:
     def __init__(self, yolo_plan: str, ufld_plan: str, device: int = 0, batch: int = 8, box_score: float = 0.4, box_nms_iou: float = 0.45,
-                 max_det: int = 1024, class_names: Optional[List[str]] = None, depth: int = 3, sets: int = 2):
+                 max_det: int = 1024, class_names: Optional[List[str]] = None, depth: int = 3, sets: int = 2, track_thresh: float = 0.5):
         self.batch, self.box_score, self.box_nms_iou, self.max_det = batch, box_score, box_nms_iou, max_det
         # `sets` independent (object engine, lane engine) pairs: consecutive batches alternate between them so the next batch's
         # kernels are already queued on the device (own streams, own activation buffers) while the previous batch drains --
@@ -52,7 +52,7 @@ class AdasPipeline:
                 e.run(batch)
                 e.run(batch)
         self._next_set = 0
-        self.tracker = BYTETracker(names=class_names or [], device=device)
+        self.tracker = BYTETracker(track_thresh=track_thresh, names=class_names or [], device=device)
         self.tracker.reset()
         self.class_names = class_names
         self._pool = ThreadPoolExecutor(max_workers=len(self.sets))
@@ -82,15 +82,19 @@ class AdasPipeline:
         TRACK_DTYPE record array of frame i (`self.tracker.messages(r.tracks[i])` gives the reference's track messages)."""
         import time
         t0 = time.perf_counter()
-        dets = []
-        for b in range(len(r.counts)):
-            n = int(r.counts[b])
-            bx = r.boxes[b, :n]
-            # demo.py:272-275 feeds RectInfo.tolist("xyxy") -> ints, and the label as class id
-            xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(int) if n else np.zeros((0, 4), int)
-            ids = r.class_ids[b, :n] if self.class_names is None else [self.class_names[c] for c in r.class_ids[b, :n]]
-            dets.append((xyxy, r.scores[b, :n], ids))
-        r.tracks = self.tracker.update_batch(dets)
+        counts = np.asarray(r.counts, np.int32)
+        keep = np.arange(r.boxes.shape[1])[None, :] < counts[:, None]            # [B, max_det] valid detections, frame-major
+        bx = r.boxes[keep]
+        # demo.py:272-275 feeds RectInfo.tolist("xyxy") -> ints (truncation), and the label as class id
+        xyxy = np.stack([bx[:, 0], bx[:, 1], bx[:, 0] + bx[:, 2], bx[:, 1] + bx[:, 3]], 1).astype(np.int64).astype(np.float64)
+        if self.class_names is None:
+            r.tracks = self.tracker.update_batch_arrays(counts, xyxy, r.scores[keep].astype(np.float64), r.class_ids[keep])
+        else:
+            cls, o, dets = r.class_ids[keep], 0, []
+            for n in counts.tolist():
+                dets.append((xyxy[o:o + n], r.scores[keep][o:o + n], [self.class_names[c] for c in cls[o:o + n]]))
+                o += n
+            r.tracks = self.tracker.update_batch(dets)
         self.track_seconds = getattr(self, "track_seconds", 0.0) + (time.perf_counter() - t0)
         self.track_batches = getattr(self, "track_batches", 0) + 1
 

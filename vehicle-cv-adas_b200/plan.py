@@ -131,22 +131,32 @@ class Weights:
 # their biases so that O(100) of the 8400 / 25200 anchors clear box_score = 0.4 and the DFL boxes vary in size.
 # The head gain sets BOTH the spread of the per-anchor scores and the size of the fp16-vs-fp32 score error (both scale with it):
 # a random network has a fixed noise-to-signal ratio (~1 % of the per-anchor logit spread after ~100 fp16 layers), so the gains
-# below are the largest that keep the probability error under the 1e-3 contract (v8l: 45, v5n: 20 -> ~7e-4 .. 8e-4)
+# below are the largest that keep the probability error under the 1e-3 contract (v8l: 16 -> 8e-4 on the device, 5.5e-4 in the CPU fp16 emulation; v5n: 20 -> 8.6e-4; at gain 45 the v8l device error is 1.5e-3)
 # and ~2-4 % of the candidates then sit within 1e-3 of the threshold.  (Tried and dropped: BatchNorm statistics measured on
 # calibration frames -- activations standardised like a trained net's -- spread the scores 14x but amplified the fp16 error 10x
 # further: max probability error 0.15, 73 px on DFL boxes.)
 SYNTH_PROFILES = {
-    "yolov8": {"gains": [(r"model\.22\.cv3\.\d\.2\.weight", 45.0), (r"model\.22\.cv2\.\d\.2\.weight", 25.0)],
-               "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -9.0)]},
+    "yolov8": {"gains": [(r"model\.22\.cv3\.\d\.2\.weight", 16.0), (r"model\.22\.cv2\.\d\.2\.weight", 25.0)],
+               "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -3.5)]},
     "yolov5": {"gains": [(r"model\.24\.m\.\d\.weight", 20.0)],
                "fill": [(r"model\.24\.m\.\d\.bias", -2.7)]},
     "ufldv2": {},
 }
 
 
-def synth_weights(kind: str, seed: int = 0, variant: Optional[str] = None) -> "Weights":
+# "workload" head for throughput runs (bench.py): a wider score distribution (scores up to ~0.9, so ByteTrack sees high- and
+# low-score detections and keeps tracks alive) at the price of a ~1.5e-3 fp16-vs-fp32 probability error; the parity tests use
+# SYNTH_PROFILES, whose scores all lie in [0.4, 0.5].
+SYNTH_PROFILES_WORKLOAD = {
+    "yolov8": {"gains": [(r"model\.22\.cv3\.\d\.2\.weight", 45.0), (r"model\.22\.cv2\.\d\.2\.weight", 25.0)],
+               "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -9.0)]},
+}
+
+
+def synth_weights(kind: str, seed: int = 0, variant: Optional[str] = None, workload: bool = False) -> "Weights":
     """Seeded synthetic weights (`variant` is accepted for call-site symmetry with the builders and ignored)."""
-    return Weights(None, seed=seed, profile=SYNTH_PROFILES[kind])
+    prof = SYNTH_PROFILES_WORKLOAD.get(kind, SYNTH_PROFILES[kind]) if workload else SYNTH_PROFILES[kind]
+    return Weights(None, seed=seed, profile=prof)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -375,59 +375,67 @@ def test_pipeline_overlapped_equals_synchronous():
 
 def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
     """End to end from FRAMES: AdasPipeline (device) against bench.CpuReferencePath (reference pre/post/tracker semantics + fp32
-    torch-CPU nets with the same weights) on 16 consecutive frames of the bench's synthetic stream.  Candidate sets, class ids, NMS
-    emission (indices incl. duplicates) and track ids must be EXACTLY equal, scores within 1e-3, boxes within 0.5 source pixel, lane
-    status equal and lane points within one pixel, on every frame whose oracle-side decisions are decisive, i.e. no candidate score
-    within 1e-3 of the threshold, no pair of candidate scores closer than 2e-3 (the NMS visits candidates by score), no NMS IoU
-    within 2e-3 of the threshold.  The indecisive fraction is printed; tracks are compared over the decisive prefix of the stream."""
+    torch-CPU nets with the same weights) on 16 consecutive frames of the bench's synthetic stream.
+    Per frame: the candidate sets (anchors clearing box_score) must be equal except for anchors whose ORACLE score lies within the
+    1e-3 contract tolerance of the threshold ("margin frame", counted and printed); on every other frame class ids, NMS emission
+    (candidate indices incl. duplicates) are EXACTLY equal, scores within 1e-3, boxes within 0.5 source pixel; track ids / activation
+    flags are compared exactly over the prefix of the stream before the first margin frame; lane status equal and lane points within
+    one pixel wherever the lane-level decisions are decisive."""
     import bench
     from adas_b200.pipeline import AdasPipeline
+    from oracle import track as otrack
     plans = {"yolov8": cached_plan("yolov8", scale="l"), "ufldv2": cached_plan("ufldv2", backbone="34")}
     cpu = bench.CpuReferencePath(plans)
     frames = bench.synth_stream(7, 16)
-    score_thr, iou_thr, track_thr = 0.42, 0.45, 0.33       # parity weights: scores lie in [0.4, 0.5] -> births need det_thresh = track_thresh + 0.1 = 0.43
-    from oracle import track as otrack
+    # the parity weights' scores lie in [0.4, 0.5]: detector threshold 0.44, tracker births at det_thresh = track_thresh + 0.1 = 0.44
+    score_thr, iou_thr, track_thr = 0.44, 0.45, 0.34
     cpu.trk = otrack.Tracker(track_thresh=track_thr)
     cpu.trk.reset()
     pipe = AdasPipeline(plans["yolov8"][0], plans["ufldv2"][0], device=0, batch=8, box_score=score_thr, box_nms_iou=iou_thr, sets=1,
                         track_thresh=track_thr)
     res = [pipe.step(frames[i:i + 8]) for i in (0, 8)]
-    pipe.close()
     geom = post.letterbox_geom(720, 1280, 640, 640)
-    decisive, prefix_ok, n_det, n_tracks_cmp = 0, True, 0, 0
+    exact, margin_frames, prefix_ok, n_det, n_tracks_cmp, n_lane_pts = 0, 0, True, 0, 0, 0
     for f in range(16):
         r, b = res[f // 8], f % 8
         blob, _ = post.yolo_prepare_input(frames[f], 640, 640)
         with torch.no_grad():
             raw = cpu.yolo(torch.from_numpy(blob)).numpy()[0]
+        raw_dev = pipe.yolo.infer(blob)[0][0]
         det = post.yolo_postprocess(raw, "v8", geom, score_thr, iou_thr)
-        mx = raw[4:].max(0)
-        cs = np.sort(mx[mx > score_thr])
-        ok = not np.any(np.abs(mx - score_thr) < 1e-3) and (len(cs) < 2 or np.diff(cs).min() > 2e-3)
-        if ok and det["n_cand"] > 1:                       # IoU margins of the NMS (+1 convention, utils.py:236-239) over all candidate pairs
-            bx, _, _ = post.yolo_process_output(raw, "v8", score_thr)
-            w = post.convert_boxes(bx, geom).astype(np.float64)
-            x1, y1, x2, y2 = w[:, 0], w[:, 1], w[:, 0] + w[:, 2], w[:, 1] + w[:, 3]
-            ar = (x2 - x1 + 1) * (y2 - y1 + 1)
-            iw = np.maximum(0, np.minimum(x2[:, None], x2[None]) - np.maximum(x1[:, None], x1[None]) + 1)
-            ih = np.maximum(0, np.minimum(y2[:, None], y2[None]) - np.maximum(y1[:, None], y1[None]) + 1)
-            iou = iw * ih / (ar[:, None] + ar[None] - iw * ih)
-            ok = not np.any(np.abs(iou[np.triu_indices(len(ar), 1)] - iou_thr) < 2e-3)
+        mx, mx_dev = raw[4:].max(0), raw_dev[4:].max(0)
+        cand, cand_dev = mx > score_thr, mx_dev > score_thr
+        assert np.abs(mx - mx_dev)[cand | cand_dev].max(initial=0.0) < 1e-3, f      # float scores within the contract
         n = int(r.counts[b])
-        if ok:
-            decisive += 1
+        if not np.array_equal(cand, cand_dev):
+            diff = cand != cand_dev
+            assert np.all(np.abs(mx[diff] - score_thr) < 1e-3), f                   # only margin anchors may flip
+            margin_frames += 1
+            ok = False
+        else:
+            ok = True
             assert int(r.n_candidates[b]) == det["n_cand"], f
             assert n == len(det["idx"]) and np.array_equal(r.cand_index[b, :n], det["idx"]), f
             assert np.array_equal(r.class_ids[b, :n], det["cls"]), f
             assert np.abs(r.scores[b, :n] - det["scores"]).max(initial=0.0) < 1e-3, f
             assert np.abs(r.boxes[b, :n] - det["boxes"]).max(initial=0.0) < 0.5, f
+            exact += 1
             n_det += n
-        # lanes: status equal, points within one pixel (argmax / existence flips are covered by test_ufldv2_engine_vs_oracle)
+        # lanes: decoded from the oracle's heads; status equal and points within a pixel when no existence flag sits on a near-tie
         x = post.ufld_prepare_input(frames[f], 320, 1600, 0.6)
         with torch.no_grad():
             heads = [o.numpy() for o in cpu.ufld(torch.from_numpy(x))]
         opts, ost, _ = post.ufld_decode(heads, 1280, 720, post.CULANE_ROW_ANCHOR, post.CULANE_COL_ANCHOR)
-        # tracker: both sides see the same detections while every frame so far was decisive
+        tie = min(float(np.abs(heads[2][0, 1] - heads[2][0, 0]).min()), float(np.abs(heads[3][0, 1] - heads[3][0, 0]).min())) < 2e-2
+        if not tie:
+            assert [bool(v) for v in r.lane_status[b]] == ost, f
+            for l in range(4):
+                m = int(r.lane_npts[b, l])
+                if m == len(opts[l]):
+                    if m:
+                        assert np.abs(r.lane_pts[b, l, :m] - np.array(opts[l], np.int32).reshape(-1, 2)).max() <= 1, (f, l)
+                    n_lane_pts += m
+        # tracker: both sides see the same detections while every frame so far was exact
         prefix_ok = prefix_ok and ok
         bxr = det["boxes"]
         xyxy = np.stack([bxr[:, 0], bxr[:, 1], bxr[:, 0] + bxr[:, 2], bxr[:, 1] + bxr[:, 3]], 1).astype(int) if len(bxr) else np.zeros((0, 4), int)
@@ -437,6 +445,7 @@ def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
             got = sorted((int(t["track_id"]), bool(t["is_activated"])) for t in r.tracks[b])
             assert got == want, (f, got, want)
             n_tracks_cmp += len(want)
-    print(f"[parity] frames -> detections/tracks vs CPU reference path: {decisive}/16 frames decisive, {n_det} detections and "
-          f"{n_tracks_cmp} track records compared exactly")
-    assert decisive >= 4 and n_det > 0
+    pipe.close()
+    print(f"[parity] frames -> detections / lanes / tracks vs the CPU reference path: {exact}/16 frames exact ({margin_frames} margin frames), "
+          f"{n_det} detections, {n_tracks_cmp} track records and {n_lane_pts} lane points compared")
+    assert exact >= 8 and n_det > 0 and n_tracks_cmp > 0

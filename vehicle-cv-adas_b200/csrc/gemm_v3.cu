@@ -30,6 +30,7 @@ static constexpr int V3_THREADS = 64 + 32 * V3_EPI_WARPS;     // 576
 static constexpr int V3_SLAB_ROWS = 136;
 static constexpr int V3_SLAB_BYTES = V3_SLAB_ROWS * BK * 2;   // 17408
 static constexpr int V3_STG_BYTES = BM * 64 * 2;              // one staging buffer: 128 rows x 64 fp16 columns
+static constexpr int V3_STG_BUFS = 3;                          // rotating staging buffers (residual in -> output out)
 static constexpr int V3_DYN_SMEM_MAX = 227 * 1024 - 3072;
 
 struct GemmV3 {
@@ -41,6 +42,7 @@ struct GemmV3 {
     int a_sub_bytes, b_bytes, stage_bytes, stages;
     int n_tiles, m_tiles, total_tiles;
     int tma_st;        // staged TMA-store epilogue (fp16, not transposed, BN % 64 == 0)
+    int res_tma;       // staged epilogue only: the residual tile of every chunk is fetched by TMA into the staging buffer
     int stg_off;       // byte offset of the two staging buffers behind the operand ring
     int pdl;
     int prefetch_w;    // fetch the first stages' weight tiles before griddepcontrol.wait
@@ -49,19 +51,20 @@ struct GemmV3 {
 };
 
 struct GemmV3Launch {
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmR;
     GemmV3 g;
 };
 
 template <bool kTmaStore>
 __global__ void __launch_bounds__(V3_THREADS, 1)
 conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                    const GemmV3 g) {
+                    const __grid_constant__ CUtensorMap tmR, const GemmV3 g) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t res_bar[V3_STG_BUFS];      // residual tile of a chunk has landed in its staging buffer
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(16) float s_bias[2][256];
 
@@ -80,6 +83,8 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         if (kTmaStore) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        if (kTmaStore && g.res_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+        for (int s = 0; s < V3_STG_BUFS; ++s) mbar_init(smem_u32(&res_bar[s]), 1);
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -255,6 +260,34 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int per_img = p.s2_tw * p.s2_th;
         const int act = (p.dbg & 8) ? 0 : p.act;
         uint32_t tile_it = 0, chunk_it = 0;
+        // Residual through the staging buffers (staged path): chunk j lives in buffer j % 3 -- its residual tile is fetched by TMA two
+        // chunks ahead (the issuer walks a prefetch cursor over (tile, sub-tile, chunk), across tile boundaries), every thread adds the
+        // 32 bytes it is about to overwrite, and the finished chunk leaves through the TMA store.  Buffer reuse: R(j+2) targets the
+        // buffer store S(j-1) read; the issuer waits for S(j-1) (`wait_group.read 1` right after committing S(j)) before issuing it.
+        const bool res_tma = kTmaStore && g.res_tma;
+        int pf_w = blockIdx.x, pf_mt = 0, pf_cc = 0;
+        uint32_t pf_j = 0;
+        auto issue_res = [&]() {
+            if (pf_w >= g.total_tiles) return;
+            const int n_t2 = pf_w % g.n_tiles, m_t2 = pf_w / g.n_tiles;
+            const uint32_t bar = smem_u32(&res_bar[pf_j % V3_STG_BUFS]);
+            const uint32_t dst = stg_base + (pf_j % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES;
+            if (p.s2) {
+                const int pi = m_t2 * g.MT + pf_mt;
+                const int b = fast_div(pi, g.fd_per_img);
+                const int rem = pi - b * per_img;
+                const int ty = fast_div(rem, g.fd_tw), tx = rem - ty * p.s2_tw;
+                mbar_expect_tx(bar, (uint32_t)(p.s2_bw * p.s2_bh * 128));
+                tma_load_4d(dst, &tmR, n_t2 * p.BN + pf_cc * 64, tx * p.s2_bw, ty * p.s2_bh, b, bar);     // out-of-range patches read zeros
+            } else {
+                mbar_expect_tx(bar, (uint32_t)V3_STG_BYTES);
+                tma_load_2d(dst, &tmR, n_t2 * p.BN + pf_cc * 64, m_t2 * BMT + pf_mt * BM, bar);
+            }
+            ++pf_j;
+            if (++pf_cc == n_chunks) { pf_cc = 0; if (++pf_mt == g.MT) { pf_mt = 0; pf_w += gridDim.x; } }
+        };
+        if (res_tma && issuer && !(p.dbg & 16)) { issue_res(); issue_res(); }
+        __syncwarp();
         for (int w = blockIdx.x; w < g.total_tiles; w += gridDim.x, ++tile_it) {
             const int as = acc2 ? (int)(tile_it & 1) : 0;
             const int bs = (int)(tile_it & 1);
@@ -313,7 +346,16 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int ncols = have ? min(16, p.N - n) : 0;      // valid columns (multiple of 8 when not transposed; may be <= 0)
                     uint4 rr[2];
                     const bool has_res = (p.res != nullptr) && row_ok && !p.transposed && ncols > 0;
-                    if (has_res) {
+                    if (res_tma) {
+                        // the residual tile of this chunk sits in the staging buffer the output will overwrite (same swizzled slots)
+                        mbar_wait(smem_u32(&res_bar[chunk_it % V3_STG_BUFS]), (chunk_it / V3_STG_BUFS) & 1u);
+                        const uint32_t rs = stg_base + (chunk_it % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES + (uint32_t)r * 128u;
+                        const uint32_t sw = (uint32_t)(r & 7);
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[0].x), "=r"(rr[0].y), "=r"(rr[0].z), "=r"(rr[0].w)
+                                     : "r"(rs + ((((uint32_t)(2 * part)) ^ sw) << 4)));
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[1].x), "=r"(rr[1].y), "=r"(rr[1].z), "=r"(rr[1].w)
+                                     : "r"(rs + ((((uint32_t)(2 * part + 1)) ^ sw) << 4)));
+                    } else if (has_res) {
                         const __half* rp = p.res + (size_t)row * res_ld + n;
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
@@ -374,19 +416,19 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
                             o[j] = row_ok ? *reinterpret_cast<const uint32_t*>(&h) : 0u;      // halo / out-of-range rows are written as zeros
                         }
-                        const uint32_t stg = stg_base + (chunk_it & 1u) * (uint32_t)V3_STG_BYTES + (uint32_t)r * 128u;
+                        const uint32_t stg = stg_base + (chunk_it % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES + (uint32_t)r * 128u;
                         const uint32_t sw = (uint32_t)(r & 7);
                         st_shared_v4(stg + ((((uint32_t)(2 * part)) ^ sw) << 4), o[0], o[1], o[2], o[3]);
                         st_shared_v4(stg + ((((uint32_t)(2 * part + 1)) ^ sw) << 4), o[4], o[5], o[6], o[7]);
                         fence_async_smem();                 // generic-proxy writes -> visible to the TMA (async proxy)
-                        if (issuer) bulk_wait_read0();      // the store that used the OTHER buffer has finished reading it (see protocol below)
+                        if (issuer) bulk_wait_read1();      // every store but the latest has finished reading shared memory (see protocol below)
                         __syncwarp();
                         asm volatile("bar.sync 1, 512;" ::: "memory");
-                        // Protocol: chunk i fills buffer i&1.  The issuer waits for ALL earlier stores to finish reading shared memory
-                        // before it arrives at barrier(i); after barrier(i) every thread therefore knows stores <= i-1 are done, and the
-                        // next write into buffer (i+1)&1 (last read by store i-1) is safe.
+                        // Protocol: chunk i fills buffer i % 3.  The issuer waits for all stores but the most recent one before it arrives at
+                        // barrier(i); after barrier(i) every thread therefore knows stores <= i-2 are done, and the next write, into buffer
+                        // (i+1) % 3 (last read by store i-2), is safe.
                         if (issuer && !(p.dbg & 4)) {
-                            const uint32_t src = stg_base + (chunk_it & 1u) * (uint32_t)V3_STG_BYTES;
+                            const uint32_t src = stg_base + (chunk_it % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES;
                             if (p.s2) {
                                 const int pi = m_t * g.MT + mt;
                                 if (pi < g.n_patches) {
@@ -399,6 +441,10 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 tma_store_2d(&tmC, src, n0 + cc * 64, m0 + mt * BM);
                             }
                             bulk_commit();
+                        }
+                        if (res_tma && issuer) {
+                            bulk_wait_read1();              // store (i-1) has left buffer (i+2) % 3 ...
+                            issue_res();                    // ... which now receives the residual tile of chunk i+2
                         }
                         __syncwarp();
                         ++chunk_it;
@@ -513,7 +559,10 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
                  (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) ? 1 : 0;
     const int b_bytes = ((p.BN * BK * 2) + 1023) & ~1023;
     g->b_bytes = b_bytes;
-    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? 2 * V3_STG_BYTES : 0);
+    static const int no_res_tma = env_int("ADAS_B200_NO_RES_TMA", 0);
+    g->res_tma = (g->tma_st && p.res != nullptr && !no_res_tma && (reinterpret_cast<uintptr_t>(p.res) & 15u) == 0 &&
+                  (p.res_ld < 0 ? -p.res_ld : p.res_ld) % 8 == 0) ? 1 : 0;
+    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? V3_STG_BUFS * V3_STG_BYTES : 0);
     g->slab = 0;
     if (p.ntaps == 9 && !p.s2 && !no_slab) {
         const int slab_stage = g->MT * V3_SLAB_BYTES + 3 * b_bytes;
@@ -543,7 +592,7 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     return 0;
 }
 
-static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? 2 * V3_STG_BYTES : 0) + 1024; }
+static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? V3_STG_BUFS * V3_STG_BYTES : 0) + 1024; }
 
 int gemm_v3_launch(const GemmV3Launch& L, cudaStream_t st) {
     int num_sms = 0;
@@ -561,8 +610,8 @@ int gemm_v3_launch(const GemmV3Launch& L, cudaStream_t st) {
     attr1.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr1;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (gp.tma_st) ADAS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_v3_kernel<true>, L.tmA, L.tmB, L.tmC, gp));
-    else ADAS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_v3_kernel<false>, L.tmA, L.tmB, L.tmC, gp));
+    if (gp.tma_st) ADAS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_v3_kernel<true>, L.tmA, L.tmB, L.tmC, L.tmR, gp));
+    else ADAS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_v3_kernel<false>, L.tmA, L.tmB, L.tmC, L.tmR, gp));
     count_launch();
     return 0;
 }
@@ -611,7 +660,7 @@ int gemm_v3_candidates(const GemmParams& base, int max_out, int* BN_out, int* mt
     return n;
 }
 
-static int make_tmap_out(CUtensorMap* tm, const GemmV3& g);
+static int make_tmap_out(CUtensorMap* tm, const GemmV3& g, const void* base, int ld);
 
 int gemm_v3_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
                     const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque) {
@@ -626,8 +675,9 @@ int gemm_v3_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, u
         delete L;
         return 1;
     }
-    L->tmC = L->tmA;
-    if (L->g.tma_st && make_tmap_out(&L->tmC, L->g)) { delete L; return 1; }
+    L->tmC = L->tmA; L->tmR = L->tmA;
+    if (L->g.tma_st && make_tmap_out(&L->tmC, L->g, L->g.p.out, L->g.p.out_ld)) { delete L; return 1; }
+    if (L->g.res_tma && make_tmap_out(&L->tmR, L->g, L->g.p.res, L->g.p.res_ld < 0 ? -L->g.p.res_ld : L->g.p.res_ld)) { delete L; return 1; }
     *opaque = L;
     return 0;
 }
@@ -642,8 +692,9 @@ int gemm_v3_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, ui
         delete L;
         return 1;
     }
-    L->tmC = L->tmA;
-    if (L->g.tma_st && make_tmap_out(&L->tmC, L->g)) { delete L; return 1; }
+    L->tmC = L->tmA; L->tmR = L->tmA;
+    if (L->g.tma_st && make_tmap_out(&L->tmC, L->g, L->g.p.out, L->g.p.out_ld)) { delete L; return 1; }
+    if (L->g.res_tma && make_tmap_out(&L->tmR, L->g, L->g.p.res, L->g.p.res_ld < 0 ? -L->g.p.res_ld : L->g.p.res_ld)) { delete L; return 1; }
     *opaque = L;
     return 0;
 }
@@ -651,13 +702,13 @@ int gemm_v3_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, ui
 // Output tensor map of the staged epilogue.  Stride-1 / dense ops: the [M, N] slice of the output matrix, box 64 columns x 128
 // rows.  Stride-2 ops: the INTERIOR of the padded output grid as a 4-D tensor [N, Wo, Ho, B], box 64 x bw x bh x 1, so partial
 // patches at the right / bottom edge are clipped by the TMA unit and the halo is never touched.
-static int make_tmap_out(CUtensorMap* tm, const GemmV3& g) {
+static int make_tmap_out(CUtensorMap* tm, const GemmV3& g, const void* base_ptr, int ld) {
     const GemmParams& p = g.p;
-    if (!p.s2) return make_tmap_2d(tm, p.out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.out_ld * 2, 64, BM);
+    if (!p.s2) return make_tmap_2d(tm, base_ptr, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)ld * 2, 64, BM);
     const uint64_t Wpo = (uint64_t)p.s2_Wo + 2, Hpo = (uint64_t)p.s2_Ho + 2;
-    const __half* base = reinterpret_cast<const __half*>(p.out) + (Wpo + 1) * (uint64_t)p.out_ld;
+    const __half* base = reinterpret_cast<const __half*>(base_ptr) + (Wpo + 1) * (uint64_t)ld;
     const uint64_t B = (uint64_t)(g.n_patches / (p.s2_tw * p.s2_th));
-    return make_tmap_4d(tm, base, (uint64_t)p.N, (uint64_t)p.s2_Wo, (uint64_t)p.s2_Ho, B, (uint64_t)p.out_ld, Wpo, Hpo, 64, (uint32_t)p.s2_bw,
+    return make_tmap_4d(tm, base, (uint64_t)p.N, (uint64_t)p.s2_Wo, (uint64_t)p.s2_Ho, B, (uint64_t)ld, Wpo, Hpo, 64, (uint32_t)p.s2_bw,
                         (uint32_t)p.s2_bh);
 }
 
@@ -669,9 +720,9 @@ int gemm_v3_grid(const void* opaque) {
 }
 void gemm_v3_describe(const void* opaque, char* out, int cap) {
     const GemmV3& g = static_cast<const GemmV3Launch*>(opaque)->g;
-    snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | v3 BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d tma_st=%d", g.p.M,
+    snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | v3 BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d tma_st=%d res_tma=%d", g.p.M,
              g.p.N, g.p.Kc * g.p.ntaps, g.p.ntaps, g.p.act, g.p.res ? (g.p.res_ld < 0 ? -1 : 1) : 0, g.p.out_f32, g.p.s2, g.p.transposed, g.p.BN, g.MT,
-             g.slab, g.stages, g.acc_stages, g.total_tiles, g.tma_st);
+             g.slab, g.stages, g.acc_stages, g.total_tiles, g.tma_st, g.res_tma);
 }
 
 }  // namespace adas

@@ -265,6 +265,7 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // 32 bytes it is about to overwrite, and the finished chunk leaves through the TMA store.  Buffer reuse: R(j+2) targets the
         // buffer store S(j-1) read; the issuer waits for S(j-1) (`wait_group.read 1` right after committing S(j)) before issuing it.
         const bool res_tma = kTmaStore && g.res_tma;
+        auto buf_of = [&](uint32_t j) -> uint32_t { return res_tma ? j % V3_STG_BUFS : (j & 1u); };     // 2 buffers suffice without a residual
         int pf_w = blockIdx.x, pf_mt = 0, pf_cc = 0;
         uint32_t pf_j = 0;
         auto issue_res = [&]() {
@@ -416,19 +417,20 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
                             o[j] = row_ok ? *reinterpret_cast<const uint32_t*>(&h) : 0u;      // halo / out-of-range rows are written as zeros
                         }
-                        const uint32_t stg = stg_base + (chunk_it % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES + (uint32_t)r * 128u;
+                        const uint32_t stg = stg_base + buf_of(chunk_it) * (uint32_t)V3_STG_BYTES + (uint32_t)r * 128u;
                         const uint32_t sw = (uint32_t)(r & 7);
                         st_shared_v4(stg + ((((uint32_t)(2 * part)) ^ sw) << 4), o[0], o[1], o[2], o[3]);
                         st_shared_v4(stg + ((((uint32_t)(2 * part + 1)) ^ sw) << 4), o[4], o[5], o[6], o[7]);
                         fence_async_smem();                 // generic-proxy writes -> visible to the TMA (async proxy)
-                        if (issuer) bulk_wait_read1();      // every store but the latest has finished reading shared memory (see protocol below)
+                        if (issuer) { if (res_tma) bulk_wait_read1(); else bulk_wait_read0(); }      // see the protocol below
                         __syncwarp();
                         asm volatile("bar.sync 1, 512;" ::: "memory");
-                        // Protocol: chunk i fills buffer i % 3.  The issuer waits for all stores but the most recent one before it arrives at
-                        // barrier(i); after barrier(i) every thread therefore knows stores <= i-2 are done, and the next write, into buffer
-                        // (i+1) % 3 (last read by store i-2), is safe.
+                        // Protocol (3 buffers, residual layers): chunk i fills buffer i % 3.  The issuer waits for all stores but the most recent
+                        // one before it arrives at barrier(i); after barrier(i) every thread therefore knows stores <= i-2 are done, and the
+                        // next write, into buffer (i+1) % 3 (last read by store i-2), is safe.  (2 buffers, no residual): the issuer waits for
+                        // ALL earlier stores, so after barrier(i) stores <= i-1 are done and buffer (i+1) & 1 may be rewritten.
                         if (issuer && !(p.dbg & 4)) {
-                            const uint32_t src = stg_base + (chunk_it % V3_STG_BUFS) * (uint32_t)V3_STG_BYTES;
+                            const uint32_t src = stg_base + buf_of(chunk_it) * (uint32_t)V3_STG_BYTES;
                             if (p.s2) {
                                 const int pi = m_t * g.MT + mt;
                                 if (pi < g.n_patches) {
@@ -562,7 +564,7 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     static const int no_res_tma = env_int("ADAS_B200_NO_RES_TMA", 0);
     g->res_tma = (g->tma_st && p.res != nullptr && !no_res_tma && (reinterpret_cast<uintptr_t>(p.res) & 15u) == 0 &&
                   (p.res_ld < 0 ? -p.res_ld : p.res_ld) % 8 == 0) ? 1 : 0;
-    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? V3_STG_BUFS * V3_STG_BYTES : 0);
+    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? (g->res_tma ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0);
     g->slab = 0;
     if (p.ntaps == 9 && !p.s2 && !no_slab) {
         const int slab_stage = g->MT * V3_SLAB_BYTES + 3 * b_bytes;
@@ -592,7 +594,7 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     return 0;
 }
 
-static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? V3_STG_BUFS * V3_STG_BYTES : 0) + 1024; }
+static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? (g.res_tma ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0) + 1024; }
 
 int gemm_v3_launch(const GemmV3Launch& L, cudaStream_t st) {
     int num_sms = 0;

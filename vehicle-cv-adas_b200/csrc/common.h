@@ -60,6 +60,7 @@ struct GemmParams {
     // bw x bh patch of output pixels of one image; s2_* describe the output grid and the input's padded height
     int s2, s2_bw, s2_bh, s2_tw, s2_th, s2_Ho, s2_Wo, s2_Hp_in;
     int transposed; // 1: out[n * out_ld + row] (swap-AB FC: rows = features, cols = batch), bias per row
+    int chain;      // 1: this layer runs inside a chain launch (gemm_chain.cu): three staging buffers whatever its residual
     const float* bias;   // [N] ([M] when transposed) or nullptr
     const __half* res;   // residual, same row indexing as out, or nullptr
     void* out;
@@ -96,7 +97,14 @@ int  gemm_v3_run(void* opaque, cudaStream_t st);
 void gemm_v3_free(void* opaque);
 int  gemm_v3_grid(const void* opaque);
 void gemm_v3_describe(const void* opaque, char* out, int cap);
+void gemm_v3_tile_of(const void* opaque, int* BN, int* MT);
+bool gemm_v3_is_staged(const void* opaque);
 int  gemm_v3_candidates(const GemmParams& base, int max_out, int* BN_out, int* mt_out);
+// chain of same-shape layers in one launch (gemm_chain.cu); layer_opaques are gemm_v3_prepare results with GemmParams::chain = 1
+int  gemm_chain_prepare(void* const* layer_opaques, int n_layers, void** out);
+int  gemm_chain_run(void* opaque, cudaStream_t st);
+void gemm_chain_free(void* opaque);
+void gemm_chain_describe(const void* opaque, char* out, int cap);
 int  make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                   uint32_t box_inner, uint32_t box_rows);
 

@@ -45,6 +45,7 @@ struct Program {   // launch list for one batch size
     std::vector<std::string> step_desc;   // human-readable shape / tile choice per step (adas_engine_step_desc)
     cudaGraphExec_t graph = nullptr;
     int runs = 0;
+    int n_launch() const { int n = 0; for (uint32_t t : step_type) n += (t != 31); return n; }   // steps folded into a chain launch do not launch
 };
 
 }  // namespace adas
@@ -57,6 +58,7 @@ struct adas_engine {
     int conv_impl = 0;
     bool use_graph = true;
     bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
+    bool use_chain = true;        // ADAS_B200_CHAIN=0: one launch per layer (no gemm_chain.cu launches); read when the engine is created
     int gemm_ver = 3;             // 3 = gemm_v3.cu (product); ADAS_B200_GEMM=v2 / v1 select the round-1 kernels (A/B baselines)
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
     int mc_mode = 0;              // ADAS_B200_MC: 0 single-CTA tiles, 1 TMA-multicast pairs (measured: no gain), 2 cta_group::2 MMA pairs,
@@ -116,7 +118,77 @@ static const void* tensor_ptr(const adas_engine* e, int idx) {
     return static_cast<const uint8_t*>(e->d_blob) + e->tensors[idx].offset;
 }
 
+// one v3 GEMM step as the chain builder sees it (gemm_chain.cu)
+struct GemmRec {
+    size_t step;                       // index into Program::steps
+    GemmParams g;                      // with the tile shape that was finally chosen
+    int a_buf, a_coff, out_buf, out_coff, res_buf, res_coff;
+    bool eligible;
+    std::function<int(const GemmParams&, void**)> prep;
+};
+
+static bool chain_edge_ok(const GemmRec& a, const GemmRec& b) {
+    if (!a.eligible || !b.eligible || b.step != a.step + 1) return false;
+    const GemmParams &x = a.g, &y = b.g;
+    if (x.M != y.M || x.N != y.N || x.Kc != y.Kc || x.ntaps != y.ntaps || x.act != y.act || x.Wp != y.Wp || x.mask_H != y.mask_H || x.mask_W != y.mask_W) return false;
+    if (b.a_buf != a.out_buf || b.a_coff != a.out_coff || y.Kc != x.N) return false;        // b reads exactly what a wrote
+    if (b.res_buf >= 0 && !(b.res_buf == a.a_buf && b.res_coff == a.a_coff)) return false;     // residual = the previous layer's input
+    return true;
+}
+
+static int build_chains(adas_engine* e, Program* prog, std::vector<GemmRec>& recs) {
+    if (!e->use_chain) return 0;
+    size_t i = 0;
+    while (i < recs.size()) {
+        size_t j = i;
+        while (j + 1 < recs.size() && chain_edge_ok(recs[j], recs[j + 1])) {
+            // no layer may write a view an earlier layer of the chain still reads
+            bool clash = false;
+            const GemmRec& w = recs[j + 1];
+            for (size_t k = i; k <= j && !clash; ++k) {
+                const GemmRec& r = recs[k];
+                auto overlap = [&](int buf, int coff, int C) { return buf == w.out_buf && coff < w.out_coff + w.g.N && w.out_coff < coff + C; };
+                clash = overlap(r.a_buf, r.a_coff, r.g.Kc) || (r.res_buf >= 0 && overlap(r.res_buf, r.res_coff, r.g.N));
+            }
+            if (clash) break;
+            ++j;
+        }
+        if (j > i) {
+            std::vector<void*> layers;
+            bool ok = true;
+            for (size_t k = i; k <= j && ok; ++k) {
+                GemmParams gc = recs[k].g;
+                gc.BN = recs[i].g.BN; gc.mt_hint = recs[i].g.mt_hint; gc.chain = 1;
+                void* op = nullptr;
+                if (recs[k].prep(gc, &op)) ok = false; else layers.push_back(op);
+            }
+            void* chain = nullptr;
+            if (ok && gemm_chain_prepare(layers.data(), (int)layers.size(), &chain)) ok = false;
+            for (void* op : layers) gemm_v3_free(op);                    // the chain keeps its own copies of the tensor maps
+            if (ok) {
+                std::shared_ptr<void> keep(chain, gemm_chain_free);
+                char d[256];
+                gemm_chain_describe(chain, d, sizeof(d));
+                prog->step_desc.resize(prog->steps.size());
+                prog->step_desc[recs[i].step] = d;
+                prog->steps[recs[i].step] = [keep](cudaStream_t st) { return gemm_chain_run(keep.get(), st); };
+                for (size_t k = i + 1; k <= j; ++k) {
+                    prog->steps[recs[k].step] = [](cudaStream_t) { return 0; };   // folded into the chain launch above
+                    prog->step_type[recs[k].step] = 31;
+                    prog->step_desc[recs[k].step] = "(in the chain above)";
+                }
+            } else {
+                static const bool chain_log = getenv("ADAS_B200_CHAIN_LOG") != nullptr;
+                if (chain_log) fprintf(stderr, "[chain] steps %zu..%zu stay separate: %s\n", recs[i].step, recs[j].step, g_err);
+            }
+        }
+        i = j + 1;
+    }
+    return 0;
+}
+
 static int build_program(adas_engine* e, int batch, Program* prog) {
+    std::vector<GemmRec> recs;
     for (size_t oi = 0; oi < e->ops.size(); ++oi) {
         const PlanOp& op = e->ops[oi];
         const int32_t* p = op.p;
@@ -222,9 +294,9 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 if (e->conv_impl == 0 && e->gemm_ver == 3) {
                     // ---- product path: gemm_v3.cu ----
                     void* opaque = nullptr;
-                    auto prep = [&](const GemmParams& gc, void** out) -> int {
-                        if (s2) return gemm_v3_prepare_s2(gc, aptr, (uint64_t)Kc, (uint64_t)ab.W + 2, (uint64_t)ab.H + 2, (uint64_t)batch, (uint64_t)ab.C, opB,
-                                                          b_inner, b_rows_u, b_stride, out);
+                    const uint64_t a_Wp = (uint64_t)ab.W + 2, a_Hp = (uint64_t)ab.H + 2, a_ldC = (uint64_t)ab.C;
+                    std::function<int(const GemmParams&, void**)> prep = [=](const GemmParams& gc, void** out) -> int {
+                        if (s2) return gemm_v3_prepare_s2(gc, aptr, (uint64_t)Kc, a_Wp, a_Hp, (uint64_t)batch, a_ldC, opB, b_inner, b_rows_u, b_stride, out);
                         return gemm_v3_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, out);
                     };
                     if (!transposed && p[15] <= 0) {
@@ -267,6 +339,17 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                         gemm_v3_describe(opaque, d, sizeof(d));
                         prog->step_desc.resize(prog->step_type.size());
                         prog->step_desc.back() = d;
+                    }
+                    {
+                        GemmRec rec;
+                        rec.step = prog->steps.size();
+                        rec.g = g;
+                        gemm_v3_tile_of(opaque, &rec.g.BN, &rec.g.mt_hint);
+                        rec.a_buf = a_buf; rec.a_coff = a_coff; rec.out_buf = out_buf; rec.out_coff = out_coff; rec.res_buf = res_buf; rec.res_coff = res_coff;
+                        rec.eligible = !s2 && !transposed && ob.dtype == 0 && masked && (ntaps == 1 || ntaps == 9) && N % 64 == 0 && rec.g.BN % 64 == 0 &&
+                                       gemm_v3_is_staged(opaque);
+                        rec.prep = prep;
+                        recs.push_back(rec);
                     }
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_v3_run(keep.get(), st); });
                 } else if (e->conv_impl == 0 && !e->gemm_v1) {
@@ -399,7 +482,8 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 ADAS_CHECK(false, "plan op %zu has unknown type %u", oi, op.type);
         }
     }
-    return 0;
+    prog->step_desc.resize(prog->steps.size());
+    return build_chains(e, prog, recs);
 }
 
 // run the network for `batch` images already staged in buffer 0 (fp16 padded NHWC image)
@@ -413,7 +497,7 @@ static int run_plan(adas_engine* e, int batch) {
     Program& pg = it->second;
     if (pg.graph != nullptr) {
         ADAS_CUDA(cudaGraphLaunch(pg.graph, e->stream));
-        count_launch((int)pg.steps.size());
+        count_launch(pg.n_launch());
         return 0;
     }
     if (e->use_graph && pg.runs >= 1) {
@@ -543,6 +627,8 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     const char* gv = getenv("ADAS_B200_GEMM");
     e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
     e->gemm_ver = (gv && strcmp(gv, "v1") == 0) ? 1 : (gv && strcmp(gv, "v2") == 0) ? 2 : 3;
+    const char* ch = getenv("ADAS_B200_CHAIN");
+    e->use_chain = !(ch && ch[0] == '0');
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
     const char* mcv = getenv("ADAS_B200_MC");
@@ -1075,7 +1161,7 @@ int adas_engine_time_ops(adas_engine* e, int batch, unsigned type_mask, int iter
         for (int r = 0; r < reps; ++r) {
             n = 0;
             for (size_t i = 0; i < pg.steps.size(); ++i)
-                if (type_mask & (1u << pg.step_type[i])) { if (pg.steps[i](e->stream)) return 1; ++n; }
+                if (pg.step_type[i] != 31 && (type_mask & (1u << pg.step_type[i]))) { if (pg.steps[i](e->stream)) return 1; ++n; }
         }
     }
     ADAS_CUDA(cudaEventRecord(b, e->stream));

@@ -22,38 +22,9 @@
 #include <string.h>
 #include <mutex>
 #include "tc_common.cuh"
+#include "gemm_v3.h"
 
 namespace adas {
-
-static constexpr int V3_EPI_WARPS = 16;
-static constexpr int V3_THREADS = 64 + 32 * V3_EPI_WARPS;     // 576
-static constexpr int V3_SLAB_ROWS = 136;
-static constexpr int V3_SLAB_BYTES = V3_SLAB_ROWS * BK * 2;   // 17408
-static constexpr int V3_STG_BYTES = BM * 64 * 2;              // one staging buffer: 128 rows x 64 fp16 columns
-static constexpr int V3_STG_BUFS = 3;                          // rotating staging buffers (residual in -> output out)
-static constexpr int V3_DYN_SMEM_MAX = 227 * 1024 - 3072;
-
-struct GemmV3 {
-    GemmParams p;
-    int MT;            // 1..4 sub-tiles of 128 rows (stride-2: output patches) per CTA tile; they share every weight tile
-    int sub_cols;      // TMEM columns per sub-tile accumulator
-    int acc_stages;    // 2 when two accumulator sets fit in 512 TMEM columns
-    int slab;          // 3x3 stride-1: one 136-row activation slab per (dy, k-block) feeds the three dx taps
-    int a_sub_bytes, b_bytes, stage_bytes, stages;
-    int n_tiles, m_tiles, total_tiles;
-    int tma_st;        // staged TMA-store epilogue (fp16, not transposed, BN % 64 == 0)
-    int res_tma;       // staged epilogue only: the residual tile of every chunk is fetched by TMA into the staging buffer
-    int stg_off;       // byte offset of the two staging buffers behind the operand ring
-    int pdl;
-    int prefetch_w;    // fetch the first stages' weight tiles before griddepcontrol.wait
-    int n_patches;     // stride-2: batch * s2_tw * s2_th
-    FastDiv fd_img, fd_wp, fd_per_img, fd_tw, fd_bw;   // divisors of the epilogue's row arithmetic
-};
-
-struct GemmV3Launch {
-    CUtensorMap tmA, tmB, tmC, tmR;
-    GemmV3 g;
-};
 
 template <bool kTmaStore>
 __global__ void __launch_bounds__(V3_THREADS, 1)
@@ -540,6 +511,8 @@ static FastDiv make_fastdiv(int d) {
     return f;
 }
 
+int v3_num_sms(int* num_sms) { return v3_device_state(num_sms); }
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -564,7 +537,7 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     static const int no_res_tma = env_int("ADAS_B200_NO_RES_TMA", 0);
     g->res_tma = (g->tma_st && p.res != nullptr && !no_res_tma && (reinterpret_cast<uintptr_t>(p.res) & 15u) == 0 &&
                   (p.res_ld < 0 ? -p.res_ld : p.res_ld) % 8 == 0) ? 1 : 0;
-    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? (g->res_tma ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0);
+    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? ((g->res_tma || p.chain) ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0);
     g->slab = 0;
     if (p.ntaps == 9 && !p.s2 && !no_slab) {
         const int slab_stage = g->MT * V3_SLAB_BYTES + 3 * b_bytes;
@@ -720,6 +693,11 @@ int gemm_v3_grid(const void* opaque) {
     const int n = static_cast<const GemmV3Launch*>(opaque)->g.total_tiles;
     return n < 148 ? n : 148;
 }
+void gemm_v3_tile_of(const void* opaque, int* BN, int* MT) {
+    const GemmV3& g = static_cast<const GemmV3Launch*>(opaque)->g;
+    *BN = g.p.BN; *MT = g.MT;
+}
+bool gemm_v3_is_staged(const void* opaque) { return static_cast<const GemmV3Launch*>(opaque)->g.tma_st != 0; }
 void gemm_v3_describe(const void* opaque, char* out, int cap) {
     const GemmV3& g = static_cast<const GemmV3Launch*>(opaque)->g;
     snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | v3 BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d tma_st=%d res_tma=%d", g.p.M,

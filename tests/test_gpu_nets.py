@@ -492,11 +492,21 @@ def test_chain_launches_equal_per_layer_launches(kind, kw, B):
     assert not any("chain of" in d for d in desc_ref)
     if kind != "yolov5":
         assert n_chain >= 4 and n_folded >= 20
+    def first_buffer_mismatch():
+        """diagnostic: the first activation buffer (plan order) that differs between the two engines, with the rows concerned"""
+        _, _, pb = cached_plan(kind, **kw)
+        for bi, (rows, C, dt, H, W, _) in enumerate(pb.buffers):
+            a, b = eng.read_buffer(bi, B), ref_eng.read_buffer(bi, B)
+            if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+                bad = np.nonzero((a != b).reshape(a.shape[0], -1).any(1))[0]
+                cols = np.nonzero((a != b).reshape(-1, a.shape[-1]).any(0))[0]
+                return (f"buffer {bi} (rows/img {rows}, C {C}, HxW {H}x{W}): {len(bad)} of {a.shape[0]} rows differ, first rows {bad[:12].tolist()}, "
+                        f"last {bad[-4:].tolist()}, columns {cols.min()}..{cols.max()}, max |diff| {np.abs(a.astype(np.float32) - b.astype(np.float32)).max():.4g}")
+        return "no activation buffer differs"
+
     for rep in range(25):
         out = eng.infer(x)
         for a, b in zip(out, ref):
-            assert np.array_equal(a, b), f"replay {rep}: chain launch result differs from per-layer launches"
-    # every activation buffer, not just the heads
-    nb = eng.num_buffers() if hasattr(eng, "num_buffers") else 0
+            assert np.array_equal(a, b), f"replay {rep}: chain launch result differs from per-layer launches; {first_buffer_mismatch()}"
     ref_eng.close()
     eng.close()

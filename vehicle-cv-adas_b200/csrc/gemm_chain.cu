@@ -119,18 +119,11 @@ conv_chain_v3_kernel(const GemmV3 g, const ChainLayer* __restrict__ layers, int 
             uint32_t s = 0, ph = 0, ss = 0, sph = 0;
             int item = (int)atomicAdd(ctl, 1u);
             while (true) {
-                // hand the item to the MMA and epilogue warps
-                mbar_wait(smem_u32(&sched_empty[ss]), sph ^ 1u);
-                *reinterpret_cast<volatile int*>(&sched_item[ss]) = item;
-                mbar_arrive(smem_u32(&sched_full[ss]));
-                if (++ss == SCHED_SLOTS) { ss = 0; sph ^= 1u; }
-                if (item >= total_items) break;
-                const int next = (int)atomicAdd(ctl, 1u);            // claimed now, so its latency hides behind this item's loads
                 const int l = item / g.total_tiles, t = item - l * g.total_tiles;
                 const int n_t = t % g.n_tiles, m_t = t / g.n_tiles;
                 const int n0 = n_t * p.BN, m0 = m_t * BMT;
-                const ChainLayer* L = layers + l;
-                if (l > 0) {
+                const ChainLayer* L = layers + (item < total_items ? l : 0);
+                if (item < total_items && l > 0) {
                     // the row blocks this tile reads have been stored by every column tile of the previous layer
                     const uint32_t* fl = flags + (size_t)(l - 1) * n_rb;
                     int lo = (m0 - halo) / BM, hi = (m0 + BMT - 1 + halo) / BM;
@@ -140,6 +133,14 @@ conv_chain_v3_kernel(const GemmV3 g, const ChainLayer* __restrict__ layers, int 
                         while ((int32_t)(ld_acquire_u32(fl + rb) - flag_target) < 0) __nanosleep(32);
                     fence_proxy_async_all();
                 }
+                // hand the item to the MMA and epilogue warps -- only now: the epilogue requests the residual tile (the previous layer's
+                // input) as soon as it sees the item, and that data is only guaranteed once this tile's row blocks are complete
+                mbar_wait(smem_u32(&sched_empty[ss]), sph ^ 1u);
+                *reinterpret_cast<volatile int*>(&sched_item[ss]) = item;
+                mbar_arrive(smem_u32(&sched_full[ss]));
+                if (++ss == SCHED_SLOTS) { ss = 0; sph ^= 1u; }
+                if (item >= total_items) break;
+                const int next = (int)atomicAdd(ctl, 1u);            // claimed now, so its latency hides behind this item's loads
                 for (int o = 0; o < o_cnt; ++o) {
                     for (int kc = 0; kc < p.kpt; ++kc) {
                         for (int in = 0; in < i_cnt; ++in) {
@@ -251,6 +252,7 @@ conv_chain_v3_kernel(const GemmV3 g, const ChainLayer* __restrict__ layers, int 
                 tma_load_2d(dst, &L->tmR, n0 + cc2 * 64, m0 + mt2 * BM, bar);
             };
             if (res_mode != 0 && issuer) {
+                fence_proxy_async_all();          // ordered after the producer warp's acquire of this tile's row-block counters
                 issue_res(0);
                 if (chunks_per_tile > 1) issue_res(1);
             }

@@ -491,7 +491,7 @@ def test_chain_launches_equal_per_layer_launches(kind, kw, B):
     print(f"[chain] {kind}: {n_chain} chain launches fold {n_folded + n_chain} layers ({len(descs)} plan steps)")
     assert not any("chain of" in d for d in desc_ref)
     if kind != "yolov5":
-        assert n_chain >= 4 and n_folded >= 20
+        assert n_chain >= 3 and n_folded >= 20
     def first_buffer_mismatch():
         """diagnostic: the first activation buffer (plan order) that differs between the two engines, with the rows concerned"""
         _, _, pb = cached_plan(kind, **kw)

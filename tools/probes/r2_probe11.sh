@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 probe 11: chain launches (gemm_chain.cu) -- correctness vs per-layer launches, then A/B timing in the same box
 O=gpurun_out/probe11; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_nets.py -m gpu -x -q --timeout 300 -s -k "chain_launches" > $O/pytest_chain.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_nets.py -m gpu -q --timeout 300 -s -k "chain_launches" > $O/pytest_chain.txt 2>&1
 echo "chain rc=$?" >> $O/pytest_chain.txt
 grep -E "chain\]|passed|failed|^E  |FAILED|Timeout|rc=" $O/pytest_chain.txt | tail -20
 if grep -q "passed" $O/pytest_chain.txt && ! grep -q "failed" $O/pytest_chain.txt; then

@@ -482,9 +482,10 @@ def test_chain_launches_equal_per_layer_launches(kind, kw, B):
         ref = ref_eng.infer(x)
         n_ref = ref_eng.num_steps(B)
         desc_ref = [ref_eng.time_step(B, i, 1)[2] for i in range(n_ref)]
+        os.environ["ADAS_B200_CHAIN"] = "1"         # chain every eligible run (the default keeps a chain only where it timed faster)
+        eng = _capi.Engine(path, 0, max_batch=B)
     finally:
         os.environ.pop("ADAS_B200_CHAIN", None)
-    eng = _capi.Engine(path, 0, max_batch=B)
     descs = [eng.time_step(B, i, 1)[2] for i in range(eng.num_steps(B))]
     n_chain = sum("chain of" in d for d in descs)
     n_folded = sum("in the chain above" in d for d in descs)

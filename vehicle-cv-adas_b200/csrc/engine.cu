@@ -58,7 +58,8 @@ struct adas_engine {
     int conv_impl = 0;
     bool use_graph = true;
     bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
-    bool use_chain = true;        // ADAS_B200_CHAIN=0: one launch per layer (no gemm_chain.cu launches); read when the engine is created
+    int use_chain = 2;            // ADAS_B200_CHAIN: 0 = one launch per layer, 1 = chain every eligible run, default 2 = chain a run only where the
+                                  // chain launch (gemm_chain.cu) timed faster than its per-layer launches when the program was built
     int gemm_ver = 3;             // 3 = gemm_v3.cu (product); ADAS_B200_GEMM=v2 / v1 select the round-1 kernels (A/B baselines)
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
     int mc_mode = 0;              // ADAS_B200_MC: 0 single-CTA tiles, 1 TMA-multicast pairs (measured: no gain), 2 cta_group::2 MMA pairs,
@@ -154,21 +155,65 @@ static int build_chains(adas_engine* e, Program* prog, std::vector<GemmRec>& rec
             ++j;
         }
         if (j > i) {
-            std::vector<void*> layers;
-            bool ok = true;
-            for (size_t k = i; k <= j && ok; ++k) {
-                GemmParams gc = recs[k].g;
-                gc.BN = recs[i].g.BN; gc.mt_hint = recs[i].g.mt_hint; gc.chain = 1;
-                void* op = nullptr;
-                if (recs[k].prep(gc, &op)) ok = false; else layers.push_back(op);
+            static const bool chain_log = getenv("ADAS_B200_CHAIN_LOG") != nullptr;
+            // tile shapes worth trying for the chain: the ones the member layers chose for themselves
+            std::vector<std::pair<int, int>> shapes;
+            for (size_t k = i; k <= j; ++k) {
+                const std::pair<int, int> sh(recs[k].g.BN, recs[k].g.mt_hint);
+                if (std::find(shapes.begin(), shapes.end(), sh) == shapes.end()) shapes.push_back(sh);
             }
-            void* chain = nullptr;
-            if (ok && gemm_chain_prepare(layers.data(), (int)layers.size(), &chain)) ok = false;
-            for (void* op : layers) gemm_v3_free(op);                    // the chain keeps its own copies of the tensor maps
-            if (ok) {
-                std::shared_ptr<void> keep(chain, gemm_chain_free);
+            const bool timed = e->use_chain == 2 && e->autotune;
+            if (!timed) shapes.resize(1);
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            float best_ms = 1e30f;
+            if (timed) {
+                // the alternative: the per-layer launches as they stand, back to back
+                ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1));
+                int rc = 0;
+                for (int r = 0; r < 5 && !rc; ++r) {
+                    if (r == 1) cudaEventRecord(ev0, e->stream);
+                    for (size_t k = i; k <= j && !rc; ++k) rc = prog->steps[recs[k].step](e->stream);
+                }
+                cudaEventRecord(ev1, e->stream);
+                if (rc || cudaEventSynchronize(ev1) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ADAS_CHECK(false, "chain timing: per-layer launches failed (%s)", g_err); }
+                cudaEventElapsedTime(&best_ms, ev0, ev1);
+                if (chain_log) fprintf(stderr, "[chain] steps %zu..%zu per-layer launches: %.1f us\n", recs[i].step, recs[j].step, best_ms * 250.0);
+            }
+            void* best_chain = nullptr;
+            for (const auto& sh : shapes) {
+                std::vector<void*> layers;
+                bool ok = true;
+                for (size_t k = i; k <= j && ok; ++k) {
+                    GemmParams gc = recs[k].g;
+                    gc.BN = sh.first; gc.mt_hint = sh.second; gc.chain = 1;
+                    void* op = nullptr;
+                    if (recs[k].prep(gc, &op)) ok = false; else layers.push_back(op);
+                }
+                void* chain = nullptr;
+                if (ok && gemm_chain_prepare(layers.data(), (int)layers.size(), &chain)) ok = false;
+                for (void* op : layers) gemm_v3_free(op);                    // the chain keeps its own copies of the tensor maps
+                if (!ok) {
+                    if (chain_log) fprintf(stderr, "[chain] steps %zu..%zu BN=%d MT=%d not chainable: %s\n", recs[i].step, recs[j].step, sh.first, sh.second, g_err);
+                    continue;
+                }
+                if (!timed) { best_chain = chain; break; }
+                int rc = 0;
+                for (int r = 0; r < 5 && !rc; ++r) {
+                    if (r == 1) cudaEventRecord(ev0, e->stream);
+                    rc = gemm_chain_run(chain, e->stream);
+                }
+                cudaEventRecord(ev1, e->stream);
+                float ms = 1e30f;
+                if (!rc && cudaEventSynchronize(ev1) == cudaSuccess) cudaEventElapsedTime(&ms, ev0, ev1);
+                if (chain_log) fprintf(stderr, "[chain] steps %zu..%zu one launch BN=%d MT=%d: %.1f us\n", recs[i].step, recs[j].step, sh.first, sh.second, ms * 250.0);
+                if (ms < best_ms * 0.98f) { best_ms = ms; if (best_chain) gemm_chain_free(best_chain); best_chain = chain; }
+                else gemm_chain_free(chain);
+            }
+            if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+            if (best_chain) {
+                std::shared_ptr<void> keep(best_chain, gemm_chain_free);
                 char d[256];
-                gemm_chain_describe(chain, d, sizeof(d));
+                gemm_chain_describe(best_chain, d, sizeof(d));
                 prog->step_desc.resize(prog->steps.size());
                 prog->step_desc[recs[i].step] = d;
                 prog->steps[recs[i].step] = [keep](cudaStream_t st) { return gemm_chain_run(keep.get(), st); };
@@ -177,9 +222,6 @@ static int build_chains(adas_engine* e, Program* prog, std::vector<GemmRec>& rec
                     prog->step_type[recs[k].step] = 31;
                     prog->step_desc[recs[k].step] = "(in the chain above)";
                 }
-            } else {
-                static const bool chain_log = getenv("ADAS_B200_CHAIN_LOG") != nullptr;
-                if (chain_log) fprintf(stderr, "[chain] steps %zu..%zu stay separate: %s\n", recs[i].step, recs[j].step, g_err);
             }
         }
         i = j + 1;
@@ -628,7 +670,7 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
     e->gemm_ver = (gv && strcmp(gv, "v1") == 0) ? 1 : (gv && strcmp(gv, "v2") == 0) ? 2 : 3;
     const char* ch = getenv("ADAS_B200_CHAIN");
-    e->use_chain = !(ch && ch[0] == '0');
+    e->use_chain = !ch ? 2 : ch[0] == '0' ? 0 : ch[0] == '1' ? 1 : 2;
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
     const char* mcv = getenv("ADAS_B200_MC");

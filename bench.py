@@ -314,9 +314,15 @@ def run_b200(args):
         ms_all_u, _ = pipe.ufld.time_ops(B, 0xFFFFFFFF, 5)
         gflop_step = (GFLOP_YOLOV8L + GFLOP_UFLD34) * B
         achieved = gflop_step / (ms_y + ms_u)          # GFLOP / ms == TFLOP/s
-        traffic = None
+        # DRAM bytes per GEMM launch: measured by ncu over whole steps of THIS command (bench.py --profile-steps, caches not flushed
+        # between launches); tools/traffic_report.py turns the capture into the JSON read here.  null if the capture is absent.
+        traffic, traffic_detail = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_traffic.json")))
+            if tj.get("batch") == B:
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_detail = {k: tj.get(k) for k in ("gemm_dram_bytes_per_step", "algorithmic_bytes_per_step", "algorithmic_bytes_per_launch",
+                                                         "dram_over_algorithmic", "all_kernels_dram_bytes_per_step", "gemm_launches_per_step", "source", "command")}
         except Exception:
             pass
         cpu = cpu_baseline_sample(plans, frames=args.cpu_frames) if args.cpu_frames > 0 else None
@@ -338,8 +344,8 @@ def run_b200(args):
             "tracks_alive": len(pipe.tracker.tracked_stracks),
             "gather": ({"per_step": True, "nccl_ranks": comm.info()[0], "all_gathers": comm.info()[1], "bytes_per_rank_per_step": int(rec.nbytes)} if comm is not None else None),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"bound": "tensor", "kernel": "conv_gemm_v3_kernel (tcgen05 implicit-GEMM conv/FC, persistent, staged TMA-store epilogue)", "achieved": round(achieved, 1), "peak": peak,
-                         "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_v3_kernel + conv_chain_v3_kernel (tcgen05 implicit-GEMM conv/FC, persistent, staged TMA-store epilogue; the chain variant runs a run of same-shape layers in one launch)", "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_detail": traffic_detail,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; GEMM launches timed alone, of measured)" if peaks else "fallback 1590 (of fallback)",
                          "launches_per_step": n_y + n_u, "avg_launch_us": round(1e3 * (ms_y + ms_u) / (n_y + n_u), 2),
                          "algorithmic_gflop_per_step": round(gflop_step, 1),

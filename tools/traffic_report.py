@@ -19,7 +19,7 @@ def parse(fn):
     for r in csv.reader(open(fn, newline="")):
         if len(r) < 15 or not r[0].isdigit():
             continue
-        d = launches.setdefault(int(r[0]), {"kernel": r[4].split("(")[0].split("<")[0], "grid": r[8]})
+        d = launches.setdefault(int(r[0]), {"kernel": r[4].split("(")[0].split("<")[0].replace("void ", "").strip(), "grid": r[8]})
         d[r[12]] = float(r[14].replace(",", "")) * UNIT.get(r[13], 1.0)
     return [launches[k] for k in sorted(launches)]
 

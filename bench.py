@@ -301,7 +301,7 @@ def run_b200(args):
     if rank == 0:
         fps = world * B * K / (ms_dev / 1e3)
         fps_e2e = world * B * K / (ms_e2e / 1e3)
-        # roofline of the dominant kernel (gemm_tc_kernel): all GEMM launches of one step back to back on the engine stream
+        # roofline of the dominant kernel (conv_gemm_v3_kernel / conv_chain_v3_kernel): all GEMM launches of one step back to back on the engine stream
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -11,7 +11,7 @@ import csv, json, os, sys
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
-GEMM_KERNELS = ("conv_gemm_v3_kernel", "conv_chain_v3_kernel", "gemm_tc_v2_kernel", "gemm_tc_kernel", "fc_stream_kernel")
+GEMM_KERNELS = ("conv_gemm_v3_kernel", "conv_chain_v3_kernel", "fc_stream_kernel")
 
 
 def parse(fn):

@@ -54,8 +54,7 @@ struct GemmParams {
     int res_ld;     // row stride of res, elements; NEGATIVE = add the residual before the activation (ResNet)
     int mask_H, mask_W;  // > 0: only rows in the interior of the padded (H+2)x(W+2) grid are stored
     int dbg;        // debug switches (ADAS_B200_DBG), 0 in production
-    int mt_hint;    // v2 kernel: number of 128-row sub-tiles per CTA tile (1..4; they share each weight tile), 0 = auto
-    int mc_hint;    // v2 kernel: 1 = CTA pairs share weight tiles via TMA multicast (cluster 2x1x1); 2 = cta_group::2 MMA pairs
+    int mt_hint;    // number of 128-row sub-tiles per CTA tile (1..4; they share each weight tile), 0 = auto
     // stride-2 convs (3x3 pad 1, or 1x1) read the input through a 4-D TMA map with traversal stride 2: an M tile is a
     // bw x bh patch of output pixels of one image; s2_* describe the output grid and the input's padded height
     int s2, s2_bw, s2_bh, s2_tw, s2_th, s2_Ho, s2_Wo, s2_Hp_in;
@@ -69,21 +68,7 @@ struct GemmParams {
     const __half* Wt; int w_ld;
 };
 
-struct GemmV2;
-int  gemm_tc_v2_prepare_s2(const GemmParams& p, const void* a_base, uint64_t a_C, uint64_t a_Wp, uint64_t a_Hp, uint64_t a_B, uint64_t a_ld,
-                           const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
-int  gemm_tc_v2_prepare(const GemmParams& p, const void* a_base, uint64_t a_inner, uint64_t a_rows, uint64_t a_stride_bytes,
-                        const void* b_base, uint64_t b_inner, uint64_t b_rows, uint64_t b_stride_bytes, void** opaque);
-int  gemm_tc_v2_run(void* opaque, cudaStream_t st);
-void gemm_tc_v2_free(void* opaque);
-void gemm_tc_v2_choose(int M, int N, int Kc, int ntaps, int* BN_out, int* mt_hint_out);
-int  gemm_tc_v2_grid(const void* opaque);
-void gemm_tc_v2_describe(const void* opaque, char* out, int cap);
-int  gemm_tc_v2_candidates(int M, int N, int Kc, int ntaps, int max_out, int* BN_out, int* mt_hint_out, int pair = 0);
-int  gemm_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st);
 int  gemm_simt_launch(const GemmParams& p, cudaStream_t st);
-int  gemm_tc_smem_bytes(int BN, int stages);
-int  gemm_tc_pick_stages(int BN, int num_kb);
 int  make_tmap_4d_s2(CUtensorMap* tm, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint64_t ld_elems,
                      uint32_t box_w_src, uint32_t box_h_src);
 int  make_tmap_4d(CUtensorMap* tm, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t ld_elems, uint64_t Wp, uint64_t Hp,

@@ -57,13 +57,9 @@ struct adas_engine {
     int max_batch = 1;
     int conv_impl = 0;
     bool use_graph = true;
-    bool gemm_v1 = false;         // ADAS_B200_GEMM=v1 selects the first (non-persistent) tcgen05 kernel
     int use_chain = 2;            // ADAS_B200_CHAIN: 0 = one launch per layer, 1 = chain every eligible run, default 2 = chain a run only where the
                                   // chain launch (gemm_chain.cu) timed faster than its per-layer launches when the program was built
-    int gemm_ver = 3;             // 3 = gemm_v3.cu (product); ADAS_B200_GEMM=v2 / v1 select the round-1 kernels (A/B baselines)
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
-    int mc_mode = 0;              // ADAS_B200_MC: 0 single-CTA tiles, 1 TMA-multicast pairs (measured: no gain), 2 cta_group::2 MMA pairs,
-                                  // 3 autotune per layer between single CTAs and cta_group::2 pairs
     cudaStream_t stream = nullptr;
     PlanHeader hdr;
     std::vector<PlanBuffer> bufs;
@@ -260,10 +256,8 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 if (!transposed) {
                     g.M = a_rows;
                     g.N = N;
-                    if (BN <= 0 && !s2) {
-                        if (e->conv_impl == 0 && !e->gemm_v1) {
-                            gemm_tc_v2_choose(a_rows, N, Kc, ntaps, &BN, &g.mt_hint);
-                        } else if (N <= 256) BN = (N + 15) / 16 * 16;
+                    if (BN <= 0 && !s2) {           // a starting point only: the v3 path ranks / times its own tile candidates below
+                        if (N <= 256) BN = (N + 15) / 16 * 16;
                         else if (N % 256 == 0) BN = 256;
                         else if (N % 160 == 0) BN = 160;
                         else if (N % 128 == 0) BN = 128;
@@ -322,7 +316,6 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     break;
                 }
                 g.Kc = Kc; g.ntaps = ntaps; g.Wp = (int)ab.W + 2; g.kpt = (Kc + 63) / 64; g.BN = BN;
-                g.stages = gemm_tc_pick_stages(BN, ntaps * g.kpt);
                 g.act = act; g.out_f32 = ob.dtype == 1 ? 1 : 0;
                 g.transposed = transposed;
                 g.bias = static_cast<const float*>(tensor_ptr(e, bias_t));
@@ -333,7 +326,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 }
                 g.out = static_cast<uint8_t*>(e->dbufs[out_buf].ptr) + (size_t)out_coff * elem_size(ob.dtype);
                 if (masked) { g.mask_H = (int)ob.H; g.mask_W = (int)ob.W; ADAS_CHECK(ob.H > 0, "op %zu: masked store into a dense buffer", oi); }
-                if (e->conv_impl == 0 && e->gemm_ver == 3) {
+                if (e->conv_impl == 0) {
                     // ---- product path: gemm_v3.cu ----
                     void* opaque = nullptr;
                     const uint64_t a_Wp = (uint64_t)ab.W + 2, a_Hp = (uint64_t)ab.H + 2, a_ldC = (uint64_t)ab.C;
@@ -394,70 +387,6 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                         recs.push_back(rec);
                     }
                     prog->steps.push_back([keep](cudaStream_t st) { return gemm_v3_run(keep.get(), st); });
-                } else if (e->conv_impl == 0 && !e->gemm_v1) {
-                    void* opaque = nullptr;
-                    if (s2) {
-                        if (gemm_tc_v2_prepare_s2(g, aptr, (uint64_t)Kc, (uint64_t)ab.W + 2, (uint64_t)ab.H + 2, (uint64_t)batch, (uint64_t)ab.C,
-                                                  opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
-                    } else if (e->autotune && !transposed && p[15] <= 0) {
-                        // measure the modelled top candidates on the device once per (op, batch); every candidate accumulates in the
-                        // same K order, so the choice never changes results
-                        int cBN[16], cMT[16], cPair[16];
-                        int nc = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 12, cBN, cMT);
-                        for (int k = 0; k < nc; ++k) cPair[k] = (e->mc_mode == 1 || e->mc_mode == 2) ? e->mc_mode : 0;
-                        if (e->mc_mode == 3) {
-                            const int np = gemm_tc_v2_candidates(g.M, g.N, Kc, ntaps, 4, cBN + nc, cMT + nc, 1);
-                            for (int k = 0; k < np; ++k) cPair[nc + k] = 2;
-                            nc += np;
-                        }
-                        float best_ms = 1e30f;
-                        cudaEvent_t ev0, ev1;
-                        ADAS_CUDA(cudaEventCreate(&ev0)); ADAS_CUDA(cudaEventCreate(&ev1));
-                        for (int ci = 0; ci < nc; ++ci) {
-                            GemmParams gc = g;
-                            gc.BN = cBN[ci]; gc.mt_hint = cMT[ci];
-                            gc.mc_hint = cPair[ci];
-                            void* cand = nullptr;
-                            if (gemm_tc_v2_prepare(gc, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &cand)) continue;
-                            int rc = gemm_tc_v2_run(cand, e->stream);
-                            if (!rc) {
-                                cudaEventRecord(ev0, e->stream);
-                                for (int r = 0; r < 3 && !rc; ++r) rc = gemm_tc_v2_run(cand, e->stream);
-                                cudaEventRecord(ev1, e->stream);
-                                if (cudaEventSynchronize(ev1) != cudaSuccess) rc = 1;
-                            }
-                            float ms = 1e30f;
-                            if (!rc) cudaEventElapsedTime(&ms, ev0, ev1);
-                            static const bool at_log = getenv("ADAS_B200_AT_LOG") != nullptr;
-                            if (at_log) fprintf(stderr, "[autotune] op %zu M=%d N=%d K=%d taps=%d BN=%d mt=%d pair=%d : %.1f us\n", oi, g.M, g.N, Kc * ntaps, ntaps,
-                                                gc.BN, gc.mt_hint, gc.mc_hint, rc ? -1.0 : ms * 1000.0 / 3.0);
-                            // score: isolated latency, optionally weighted towards SM-time (CTAs x duration) because other streams'
-                            // kernels back-fill the SMs a small grid leaves free
-                            static const float at_alpha = getenv("ADAS_B200_AT_ALPHA") ? (float)atof(getenv("ADAS_B200_AT_ALPHA")) : 0.f;
-                            if (!rc) ms *= (1.f - at_alpha) + at_alpha * (float)gemm_tc_v2_grid(cand) / 148.f;
-                            if (!rc && ms < best_ms) { best_ms = ms; if (opaque) gemm_tc_v2_free(opaque); opaque = cand; }
-                            else gemm_tc_v2_free(cand);
-                        }
-                        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-                        ADAS_CHECK(opaque != nullptr, "op %zu: no GEMM tile configuration could be launched", oi);
-                    } else {
-                        g.mc_hint = (e->mc_mode == 1 || e->mc_mode == 2) ? e->mc_mode : 0;
-                        if (gemm_tc_v2_prepare(g, opA, a_inner, a_rows_u, a_stride, opB, b_inner, b_rows_u, b_stride, &opaque)) return 1;
-                    }
-                    std::shared_ptr<void> keep(opaque, gemm_tc_v2_free);
-                    {
-                        char d[256];
-                        gemm_tc_v2_describe(opaque, d, sizeof(d));
-                        prog->step_desc.resize(prog->step_type.size());
-                        prog->step_desc.back() = d;
-                    }
-                    prog->steps.push_back([keep](cudaStream_t st) { return gemm_tc_v2_run(keep.get(), st); });
-                } else if (e->conv_impl == 0) {
-                    ADAS_CHECK(!s2, "op %zu: the v1 kernel has no stride-2 mode (unset ADAS_B200_GEMM)", oi);
-                    CUtensorMap tmA, tmB;
-                    if (make_tmap_2d(&tmA, opA, a_inner, a_rows_u, a_stride, 64, 128)) return 1;
-                    if (make_tmap_2d(&tmB, opB, b_inner, b_rows_u, b_stride, 64, (uint32_t)BN)) return 1;
-                    prog->steps.push_back([tmA, tmB, g](cudaStream_t st) { return gemm_tc_launch(tmA, tmB, g, st); });
                 } else {
                     prog->steps.push_back([g](cudaStream_t st) { return gemm_simt_launch(g, st); });
                 }
@@ -666,15 +595,10 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->device = device; e->max_batch = max_batch; e->conv_impl = conv_impl;
     const char* ng = getenv("ADAS_B200_NO_GRAPH");
     e->use_graph = !(ng && ng[0] == '1');
-    const char* gv = getenv("ADAS_B200_GEMM");
-    e->gemm_v1 = gv && strcmp(gv, "v1") == 0;
-    e->gemm_ver = (gv && strcmp(gv, "v1") == 0) ? 1 : (gv && strcmp(gv, "v2") == 0) ? 2 : 3;
     const char* ch = getenv("ADAS_B200_CHAIN");
     e->use_chain = !ch ? 2 : ch[0] == '0' ? 0 : ch[0] == '1' ? 1 : 2;
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
-    const char* mcv = getenv("ADAS_B200_MC");
-    if (mcv) e->mc_mode = atoi(mcv);
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
     if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
     e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);

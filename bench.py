@@ -34,7 +34,6 @@ GFLOP_YOLOV8L = 165.1
 GFLOP_UFLD34 = 75.15
 FRAME_H, FRAME_W = 720, 1280
 BOX_SCORE, NMS_IOU, MAX_DET = 0.4, 0.45, 300
-CACHE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "adas_b200_plans")
 
 
 def synth_stream(seed: int, n: int) -> np.ndarray:
@@ -60,7 +59,7 @@ def synth_stream(seed: int, n: int) -> np.ndarray:
 def build_plans(seed: int = 0):
     import adas_b200  # noqa: F401
     from adas_b200 import plan
-    os.makedirs(CACHE, exist_ok=True)
+    CACHE = plan.cache_dir()
     out = {}
     for kind, builder, kw in (("yolov8", plan.build_yolov8, dict(scale="l")), ("ufldv2", plan.build_ufldv2, dict(backbone="34"))):
         path = os.path.join(CACHE, f"bench_{kind}_s{seed}_workload.b200w")

@@ -238,6 +238,9 @@ def ufld_decode(outs, img_w: int, img_h: int, row_anchor, col_anchor, local_widt
 
 CULANE_ROW_ANCHOR = np.linspace(0.42, 1, 72)      # ModelConfig.init_culane_config, ultrafastLaneDetectorV2.py:47-55
 CULANE_COL_ANCHOR = np.linspace(0, 1, 81)
+TUSIMPLE_ROW_ANCHOR = np.linspace(160, 710, 56) / 720   # ModelConfig.init_tusimple_config, ultrafastLaneDetectorV2.py:31-37
+TUSIMPLE_COL_ANCHOR = np.linspace(0, 1, 41)
+UFLD_ANCHORS = {"culane": (CULANE_ROW_ANCHOR, CULANE_COL_ANCHOR), "tusimple": (TUSIMPLE_ROW_ANCHOR, TUSIMPLE_COL_ANCHOR)}
 
 
 # ---------------------------------------------------------------------------------------------

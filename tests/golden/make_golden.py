@@ -140,6 +140,30 @@ def gen_ufld():
     print("ufld cases", [(k, v.shape) for k, v in res.items() if "lane" in k][:8])
 
 
+def gen_ufld_tusimple():
+    """UFLDV2_TUSIMPLE through the reference's detector: ModelConfig.init_tusimple_config (320x800, crop 0.8, 56 row anchors
+    linspace(160,710,56)/720, 41 column anchors), heads [100,56,4] / [100,41,4]."""
+    res = {}
+    holder = [None]
+    shapes = [[1, 100, 56, 4], [1, 100, 41, 4], [1, 2, 56, 4], [1, 2, 41, 4]]
+    umod.OnnxEngine = lambda p: ref_shims.FakeEngine([1, 3, 320, 800], shapes, ["loc_row", "loc_col", "exist_row", "exist_col"],
+                                                    lambda x: holder[0])
+    det = umod.UltrafastLaneDetectorV2("fake.onnx", LaneModelType.UFLDV2_TUSIMPLE, None)
+    for seed, inval in ((0, ()), (1, (2,)), (2, (0, 3))):
+        holder[0] = synth.ufld_heads(seed, ngr=100, ncr=56, ngc=100, ncc=41, invalid_lanes=inval)
+        for (h, w) in ((720, 1280), (480, 640)) if seed == 0 else ((720, 1280),):
+            fr = synth.frame(seed, h, w)
+            det.DetectFrame(fr, adjust_lanes=False)
+            key = f"s{seed}_{h}x{w}"
+            for l in range(4):
+                res[f"{key}_lane{l}"] = np.array(det.lane_info.lanes_points[l], np.int32).reshape(-1, 2)
+            res[key + "_status"] = np.array(det.lane_info.lanes_status, np.uint8)
+            res[key + "_blob_sha"] = np.frombuffer(bytes.fromhex(sha(det.engine.last_input)), np.uint8)
+            res[key + "_blob_sample"] = det.engine.last_input[0, :, ::29, ::53].copy()
+    np.savez_compressed(os.path.join(OUT, "ufld_post_tusimple.npz"), **res)
+    print("ufld tusimple cases", [(k, v.shape) for k, v in res.items() if "lane" in k][:8])
+
+
 def gen_track():
     res = {}
     for seed, nobj in ((0, 8), (1, 14), (2, 4), (3, 25)):
@@ -235,10 +259,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lite":
         gen_yolo_lite()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tusimple":
+        gen_ufld_tusimple()
+        sys.exit(0)
     gen_nms()
     gen_yolo()
     gen_yolo_lite()
     gen_ufld()
+    gen_ufld_tusimple()
     gen_track()
     gen_ufld_net_pin()
     gen_birdview()

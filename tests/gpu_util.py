@@ -1,13 +1,11 @@
 """Helpers for the GPU parity tests: padded-NHWC packing and cached plan files."""
 import os
-import tempfile
 
 import numpy as np
 
 import adas_b200  # noqa: F401
 from adas_b200 import plan
 
-CACHE = os.path.join(tempfile.gettempdir(), "adas_b200_plans")
 
 
 def to_padded(x_nchw: np.ndarray, C: int) -> np.ndarray:
@@ -31,7 +29,7 @@ def halo_is_zero(buf: np.ndarray, B: int, H: int, W: int) -> bool:
 
 def cached_plan(kind: str, seed: int = 0, **kw):
     """Build (once per process tree) the synthetic plan + return (path, Weights-like state_dict)."""
-    os.makedirs(CACHE, exist_ok=True)
+    CACHE = plan.cache_dir()
     tag = kind + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items())) + f"_s{seed}"
     path = os.path.join(CACHE, tag + ".b200w")
     variant = kw.get("scale", kw.get("backbone"))             # calibrated BatchNorm statistics exist for the tested variants

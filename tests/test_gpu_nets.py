@@ -13,7 +13,7 @@ import torch
 
 import synth
 import adas_b200  # noqa: F401
-from adas_b200 import _capi
+from adas_b200 import _capi, plan
 from adas_b200.coreEngine import B200Engine
 from gpu_util import cached_plan
 from oracle import nets, post
@@ -146,14 +146,19 @@ def test_yolov8l_fused_detect_matches_reference_postprocessing():
     eng.close()
 
 
-@pytest.mark.parametrize("backbone", ["18", "34"])
-def test_ufldv2_engine_vs_oracle(backbone):
-    path, sd, _ = cached_plan("ufldv2", backbone=backbone)
+@pytest.mark.parametrize("backbone,dataset", [("18", "culane"), ("34", "culane"), ("18", "tusimple")])
+def test_ufldv2_engine_vs_oracle(backbone, dataset):
+    """CULane (320x1600, LayerNorm before the FC) and TuSimple (320x800, no LayerNorm, 56/41 anchors, crop 0.8) geometries of
+    ModelConfig (ultrafastLaneDetectorV2.py:31-55); the plan header names the dataset and the library derives crop / anchors from it."""
+    cfg = plan.UFLD_DATASETS[dataset]
+    path, sd, _ = cached_plan("ufldv2", backbone=backbone, cfg=dataset)
     eng = _capi.Engine(path, 0, max_batch=2)
+    assert eng.meta[6] == cfg["dataset"]
     frames = np.stack([synth.frame(s) for s in (0, 1)])
-    x = _capi.ufld_preprocess(frames, (320, 1600), 0.6)
+    x = _capi.ufld_preprocess(frames, (cfg["in_h"], cfg["in_w"]), cfg["crop_ratio"])
     outs = eng.infer(x)
-    model = nets.build("ufldv2", sd, backbone=backbone)
+    model = nets.build("ufldv2", sd, backbone=backbone, **{k: v for k, v in cfg.items() if k not in ("dataset", "crop_ratio")})
+    row_anchor, col_anchor = post.UFLD_ANCHORS[dataset]
     with torch.no_grad():
         ref = [o.numpy() for o in model(torch.from_numpy(x))]
     worst = 0.0
@@ -201,11 +206,12 @@ def test_ufldv2_engine_vs_oracle(backbone):
                         c = float((e / e.sum() * np.array(ind, np.float32)).sum() + 0.5) / (loc_r.shape[0] - 1) * ext
                         assert abs(got[k] - c) <= 1e-3 * ext, (b, name, lane, k, got[k], c)
                         n_cmp += 1
-    print(f"[parity] ufld{backbone} lane coordinates: {n_cmp} anchors within 1e-3 of the extent, {n_skip} skipped as indecisive")
-    assert n_cmp > 100 and n_skip < 0.3 * (n_cmp + n_skip)
+    print(f"[parity] ufld{backbone} {dataset} lane coordinates: {n_cmp} anchors within 1e-3 of the extent, {n_skip} skipped as indecisive")
+    if dataset == "culane":
+        assert n_cmp > 100 and n_skip < 0.3 * (n_cmp + n_skip)
     # fused lane detect == reference decode applied to the device's own head tensors
     for b in range(2):
-        opts, ost, ocrd = post.ufld_decode([o[b:b + 1] for o in outs], 1280, 720, post.CULANE_ROW_ANCHOR, post.CULANE_COL_ANCHOR)
+        opts, ost, ocrd = post.ufld_decode([o[b:b + 1] for o in outs], 1280, 720, row_anchor, col_anchor)
         for l in range(4):
             n = int(npts[b, l])
             assert n == len(opts[l])
@@ -511,3 +517,32 @@ def test_chain_launches_equal_per_layer_launches(kind, kw, B):
             assert np.array_equal(a, b), f"replay {rep}: chain launch result differs from per-layer launches; {first_buffer_mismatch()}"
     ref_eng.close()
     eng.close()
+
+
+def test_two_devices_in_one_process():
+    """Function attributes (the > 48 KB dynamic shared memory opt-in of the GEMM / chain / NMS kernels) and the SM count are per device:
+    a second engine on another GPU of the same process must work and give the same bits (runs where two GPUs are visible)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs (gpurun --gpus 2)")
+    path, _, _ = cached_plan("yolov8", scale="l")
+    upath, _, _ = cached_plan("ufldv2", backbone="18", cfg="tusimple")
+    frames = np.stack([synth.frame(70 + s) for s in range(2)])
+    x = _blob(list(frames))
+    res = []
+    for dev in (0, 1):
+        eng = _capi.Engine(path, dev, max_batch=2)
+        ufl = _capi.Engine(upath, dev, max_batch=2)
+        raw = eng.infer(x)[0]
+        det = eng.yolo_detect(frames, 0.44, 0.45)
+        lanes = ufl.ufld_detect(frames)
+        trk = _capi.NativeTracker(device=dev, track_thresh=0.34)
+        n = int(det[4][0])
+        rec = trk.update(det[0][0, :n], det[1][0, :n], det[2][0, :n])
+        res.append((raw, det, lanes, rec))
+        eng.close(); ufl.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res[0][3], res[1][3])

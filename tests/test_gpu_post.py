@@ -23,12 +23,38 @@ def test_yolo_preprocess_bit_exact(hw):
 
 
 @pytest.mark.parametrize("hw", [(720, 1280), (480, 640), (1080, 1920)])
-def test_ufld_preprocess_bit_exact(hw):
+@pytest.mark.parametrize("geom", [(320, 1600, 0.6), (320, 800, 0.8)])       # CULane / TuSimple ModelConfig
+def test_ufld_preprocess_bit_exact(hw, geom):
+    in_h, in_w, crop = geom
     fr = np.stack([synth.frame(s, *hw) for s in (2, 3)])
-    blob = _capi.ufld_preprocess(fr, (320, 1600), 0.6)
+    blob = _capi.ufld_preprocess(fr, (in_h, in_w), crop)
     for b in range(2):
-        ref = post.ufld_prepare_input(fr[b], 320, 1600, 0.6)
+        ref = post.ufld_prepare_input(fr[b], in_h, in_w, crop)
         assert np.array_equal(blob[b], ref[0]), hw
+
+
+@pytest.mark.parametrize("hw", [(720, 1280), (480, 640)])
+def test_ufld_tusimple_post_matches_reference_golden(golden_dir, hw):
+    """UFLDV2_TUSIMPLE geometry (56 row anchors linspace(160,710,56)/720, 41 column anchors, 100-cell grids) against the reference's
+    own detector output (tests/golden/make_golden.py gen_ufld_tusimple)."""
+    g = np.load(os.path.join(golden_dir, "ufld_post_tusimple.npz"))
+    cases = ((0, ()), (1, (2,)), (2, (0, 3))) if hw == (720, 1280) else ((0, ()),)
+    dims = dict(ngr=100, ncr=56, ngc=100, ncc=41)
+    heads = np.stack([np.concatenate([h.ravel() for h in synth.ufld_heads(s, invalid_lanes=iv, **dims)]) for s, iv in cases])
+    pts, npts, status, coords = _capi.ufld_postprocess(heads, (100, 56, 100, 41, 4), (hw[1], hw[0]), post.TUSIMPLE_ROW_ANCHOR, post.TUSIMPLE_COL_ANCHOR)
+    for b, (s, iv) in enumerate(cases):
+        key = f"s{s}_{hw[0]}x{hw[1]}"
+        _, _, ocrd = post.ufld_decode(synth.ufld_heads(s, invalid_lanes=iv, **dims), hw[1], hw[0], post.TUSIMPLE_ROW_ANCHOR, post.TUSIMPLE_COL_ANCHOR)
+        for l in range(4):
+            gold = g[f"{key}_lane{l}"]
+            n = int(npts[b, l])
+            assert n == len(gold), (key, l)
+            c = coords[b, l, :n]
+            assert np.allclose(c, np.array(ocrd[l]), rtol=0, atol=1e-3), (key, l)
+            diff = pts[b, l, :n] - gold
+            for j in np.nonzero(diff.any(axis=1))[0]:
+                assert np.abs(diff[j]).max() == 1 and abs(c[j] - round(c[j])) < 1e-3, (key, l, j)
+        assert np.array_equal(status[b], g[key + "_status"])
 
 
 def _check_yolo(res, b, gold_box, gold_conf, gold_cls):

@@ -62,6 +62,22 @@ def test_ufld_post_matches_reference(golden_dir, key):
     assert np.array_equal(_sha(blob), g[key + "_blob_sha"])
 
 
+@pytest.mark.parametrize("key", ["s0_720x1280", "s0_480x640", "s1_720x1280", "s2_720x1280"])
+def test_ufld_tusimple_post_matches_reference(golden_dir, key):
+    """ModelConfig.init_tusimple_config (ultrafastLaneDetectorV2.py:31-37): 320x800 input, crop 0.8, 56 / 41 anchors."""
+    g = np.load(os.path.join(golden_dir, "ufld_post_tusimple.npz"))
+    seed = int(key.split("_")[0][1:])
+    h, w = [int(v) for v in key.split("_")[1].split("x")]
+    inval = {0: (), 1: (2,), 2: (0, 3)}[seed]
+    heads = synth.ufld_heads(seed, ngr=100, ncr=56, ngc=100, ncc=41, invalid_lanes=inval)
+    pts, status, _ = post.ufld_decode(heads, w, h, post.TUSIMPLE_ROW_ANCHOR, post.TUSIMPLE_COL_ANCHOR)
+    for l in range(4):
+        assert np.array_equal(np.array(pts[l], np.int32).reshape(-1, 2), g[f"{key}_lane{l}"]), (key, l)
+    assert np.array_equal(np.array(status, np.uint8), g[key + "_status"])
+    blob = post.ufld_prepare_input(synth.frame(seed, h, w), 320, 800, 0.8)
+    assert np.array_equal(_sha(blob), g[key + "_blob_sha"])
+
+
 def test_association_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "track.npz"))
     for k in range(7):

@@ -86,3 +86,78 @@ def test_plan_file_header(tmp_path):
     blob_off, blob_bytes = h[-2:]
     assert blob_off % 256 == 0 and blob_off + blob_bytes == len(raw)
     assert struct.calcsize(fmt) + n_buf * 24 + n_ops * 112 + n_t * 24 + n_out * 16 <= blob_off
+
+
+def test_tusimple_plan_geometry():
+    """UFLDV2_TUSIMPLE (ModelConfig.init_tusimple_config + configs/tusimple_res18.py): 320x800, 100x56 / 100x41 heads, no LayerNorm."""
+    W = plan.synth_weights("ufldv2", 0)
+    pb = plan.build_ufldv2(W, "18", "tusimple")
+    assert pb.meta[:7] == [100, 56, 100, 41, 4, 100 * 56 * 4 + 100 * 41 * 4 + 2 * 56 * 4 + 2 * 41 * 4, 1]
+    assert (pb.in_h, pb.in_w) == (320, 800)
+    assert not any(op[0] == plan.OP_LAYERNORM for op in pb.ops)                 # fc_norm = False: cls.0 is Identity
+    assert "cls.0.weight" not in W.state_dict
+    fc1 = [op for op in pb.ops if op[0] == plan.OP_GEMM and op[1][14] == 1][0]
+    assert fc1[1][2] == (10 + 2) * (25 + 2) * 8                                  # reads the padded 10x25x8 pool slab directly
+    assert plan.build_ufldv2(plan.synth_weights("ufldv2", 0), "34").meta[6] == 0  # CULane
+
+
+def _corrupt(raw: bytes, off: int, fmt: str, value) -> bytes:
+    b = bytearray(raw)
+    struct.pack_into(fmt, b, off, value)
+    return bytes(b)
+
+
+def test_engine_rejects_inconsistent_plans(tmp_path):
+    """Every index / offset / size of a plan is validated when it is loaded (before any device work, so this runs without a GPU):
+    a corrupt or hostile plan must produce an error naming the plan, never an out-of-bounds access."""
+    from adas_b200 import _capi
+    W = plan.synth_weights("ufldv2", 0)
+    pb = plan.build_ufldv2(W, "18", "tusimple")
+    good = tmp_path / "good.b200w"
+    pb.write(str(good))
+    raw = good.read_bytes()
+    hdr = struct.calcsize("<8sII3I4I16IQQ")
+    n_buf, n_ops = len(pb.buffers), len(pb.ops)
+    op0 = hdr + n_buf * 24
+    ten0 = op0 + n_ops * 112
+    first_gemm = next(i for i, op in enumerate(pb.ops) if op[0] == plan.OP_GEMM)
+    cases = {
+        "buffer index": _corrupt(raw, op0 + first_gemm * 112 + 4 + 4 * 11, "<i", n_buf + 7),          # out_buf of the first GEMM
+        "weight tensor index": _corrupt(raw, op0 + first_gemm * 112 + 4 + 4 * 4, "<i", 100000),
+        "channel slice": _corrupt(raw, op0 + first_gemm * 112 + 4 + 4 * 12, "<i", 1 << 20),            # out_coff
+        "tensor offset": _corrupt(raw, ten0, "<Q", 1 << 40),
+        "dataset id": _corrupt(raw, 8 + 4 * 2 + 4 * 3 + 4 * 4 + 4 * 6, "<I", 7),
+        "dataset geometry": _corrupt(raw, 8 + 4 * 2 + 4 * 3 + 4 * 4 + 4 * 6, "<I", 0),                 # TuSimple heads labelled CULane
+        "op type": _corrupt(raw, op0 + 112, "<I", 99),
+        "truncated blob": raw[:len(raw) - 4096],
+    }
+    for name, data in cases.items():
+        p = tmp_path / "bad.b200w"
+        p.write_bytes(data)
+        try:
+            _capi.Engine(str(p))
+        except Exception as e:
+            assert "plan" in str(e), (name, str(e))
+        else:
+            raise AssertionError(f"{name}: corrupt plan was accepted")
+    # the untouched file passes validation: without a GPU the only complaint left is the missing device
+    import torch
+    if not torch.cuda.is_available():
+        try:
+            _capi.Engine(str(good))
+        except Exception as e:
+            assert "no CUDA device" in str(e), str(e)
+
+
+def test_plan_cache_is_private(tmp_path, monkeypatch):
+    import os
+    d = tmp_path / "cache"
+    monkeypatch.setenv("ADAS_B200_PLAN_CACHE", str(d))
+    assert plan.cache_dir() == str(d) and (os.stat(d).st_mode & 0o777) == 0o700
+    os.chmod(d, 0o777)
+    try:
+        plan.cache_dir()
+    except Exception as e:
+        assert "private" in str(e)
+    else:
+        raise AssertionError("a world-writable plan cache must be refused")

@@ -3,7 +3,7 @@
 Reference: TrafficLaneDetector/ufldDetector/ultrafastLaneDetectorV2.py.  `DetectFrame(image, adjust_lanes)`
 keeps its contract (fills lane_info.lanes_points / lanes_status / area_points / area_status); __prepare_input
 (96-112), engine_inference (187) and __process_output (114-181) run as one device pipeline behind
-`adas_ufld_detect`.  `ModelConfig` (21-55) is kept for the CULane geometry the plan is built for.
+`adas_ufld_detect`.  `ModelConfig` (21-55) keeps the dataset geometries; the plan header names its dataset and the model type must agree.
 """
 import numpy as np
 
@@ -37,8 +37,8 @@ class UltrafastLaneDetectorV2(LaneDetectBase):
         LaneDetectBase.__init__(self, logger)
         if None not in [model_path, model_type]:
             self.model_path, self.model_type = model_path, model_type
-        if self.model_type != LaneModelType.UFLDV2_CULANE:
-            # the reference also rejects CurveLanes (ultrafastLaneDetectorV2.py:69-72); TuSimple plans are not packed yet
+        if self.model_type not in [LaneModelType.UFLDV2_TUSIMPLE, LaneModelType.UFLDV2_CULANE]:
+            # same rejection as the reference (ultrafastLaneDetectorV2.py:69-72): CurveLanes has a config but no detector
             if self.logger:
                 self.logger.error("UltrafastLaneDetectorV2 can't use %s type." % self.model_type.name)
             raise Exception("UltrafastLaneDetectorV2 can't use %s type." % self.model_type.name)
@@ -56,6 +56,12 @@ class UltrafastLaneDetectorV2(LaneDetectBase):
         self.set_output_details(self.engine)
         if len(self.output_names) != 4:
             raise Exception("Output dims is error, please check model. load %d channels not match 4." % len(self.output_names))
+        # the plan carries its dataset (header meta[6]: 0 CULane, 1 TuSimple); crop ratio and anchors follow from it inside the library,
+        # so a model_type that names the other dataset would silently use the wrong geometry in the reference -- here it is an error
+        want = 1 if self.model_type == LaneModelType.UFLDV2_TUSIMPLE else 0
+        got = self.engine.handle.meta[6]
+        if got != want:
+            raise Exception("UltrafastLaneDetectorV2: plan %s was packed for dataset id %d, model_type %s needs %d." % (model_path, got, self.model_type.name, want))
 
     def DetectFrames(self, frames):
         """Batched extension: list of (lanes_points object-array, lanes_status list[bool]) per frame."""

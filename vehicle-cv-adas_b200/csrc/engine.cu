@@ -84,6 +84,7 @@ struct adas_engine {
     double* d_col_anchor = nullptr;
     int32_t* d_pts = nullptr; int32_t* d_npts = nullptr; uint8_t* d_status = nullptr; double* d_coords = nullptr;
     int ufld_max_pts = 0;
+    double ufld_crop = 0.6;       // crop ratio of the plan's dataset (ModelConfig.crop_ratio)
     std::vector<int32_t> h_ncand;
     cudaEvent_t ev_frames = nullptr;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -585,6 +586,112 @@ const char* adas_last_error(void) { return adas::g_err; }
 int adas_version(void) { return 100; }
 int64_t adas_launch_count(void) { return (int64_t)adas::g_launches.load(); }
 
+// UFLDv2 dataset geometry (ModelConfig, ultrafastLaneDetectorV2.py:20-55).  The plan header names the dataset (meta[6]); crop ratio and
+// anchors follow from it exactly as in the reference's ModelConfig -- they are not free parameters of a plan.
+struct UfldDataset { int id; const char* name; int in_h, in_w, ngr, ncr, ngc, ncc; double crop, r0, r1, rdiv, c0, c1; };
+static const UfldDataset kUfldDatasets[] = {
+    {0, "CULane",   320, 1600, 200, 72, 100, 81, 0.6, 0.42, 1.0, 1.0, 0.0, 1.0},        // init_culane_config (47-55)
+    {1, "TuSimple", 320,  800, 100, 56, 100, 41, 0.8, 160.0, 710.0, 720.0, 0.0, 1.0},   // init_tusimple_config (31-37): linspace(160,710,56)/720
+};
+static const UfldDataset* ufld_dataset(const PlanHeader& h) {
+    for (const UfldDataset& d : kUfldDatasets)
+        if ((int)h.meta[6] == d.id) return &d;
+    return nullptr;
+}
+
+// Every index, offset and size of a plan file is checked before anything is allocated or launched: a plan is input data (the
+// reference trusts its .trt / .onnx files to TensorRT / ONNXRuntime, which validate them; here that job is ours).
+static int validate_plan(const adas_engine* e, uint64_t file_bytes, const char* path) {
+    const PlanHeader& h = e->hdr;
+    const uint64_t rec_bytes = sizeof(PlanHeader) + (uint64_t)h.n_buffers * sizeof(PlanBuffer) + (uint64_t)h.n_ops * sizeof(PlanOp) +
+                               (uint64_t)h.n_tensors * sizeof(PlanTensor) + (uint64_t)h.n_outputs * sizeof(PlanOutput);
+    ADAS_CHECK(h.blob_offset >= rec_bytes && h.blob_offset <= file_bytes && h.blob_bytes <= file_bytes - h.blob_offset,
+               "plan %s: weight blob [%llu, +%llu) lies outside the file (%llu bytes)", path, (unsigned long long)h.blob_offset,
+               (unsigned long long)h.blob_bytes, (unsigned long long)file_bytes);
+    ADAS_CHECK(h.in_c >= 1 && h.in_c <= 4 && h.in_h >= 32 && h.in_h <= 8192 && h.in_w >= 32 && h.in_w <= 8192, "plan %s: bad input binding %ux%ux%u", path, h.in_c, h.in_h, h.in_w);
+    ADAS_CHECK(h.n_outputs >= 1, "plan %s: no outputs", path);
+    const int nb = (int)h.n_buffers, nt = (int)h.n_tensors;
+    for (int i = 0; i < nb; ++i) {
+        const PlanBuffer& b = e->bufs[i];
+        ADAS_CHECK(b.rows_per_img >= 1 && b.C >= 1 && b.C <= (1u << 20) && b.dtype <= 1 && (uint64_t)b.rows_per_img * b.C <= (1ull << 31), "plan %s: buffer %d has a bad shape", path, i);
+        ADAS_CHECK((b.H == 0 && b.W == 0) || (b.H >= 1 && b.W >= 1 && (uint64_t)(b.H + 2) * (b.W + 2) == b.rows_per_img), "plan %s: buffer %d: rows_per_img != (H+2)*(W+2)", path, i);
+    }
+    for (int i = 0; i < nt; ++i) {
+        const PlanTensor& t = e->tensors[i];
+        ADAS_CHECK(t.offset <= h.blob_bytes && t.bytes <= h.blob_bytes - t.offset && t.offset % 16 == 0 && t.dtype <= 1, "plan %s: tensor %d lies outside the weight blob", path, i);
+    }
+    auto buf_ok = [&](int b) { return b >= 0 && b < nb; };
+    auto view_ok = [&](int b, int coff, int C) { return buf_ok(b) && coff >= 0 && C >= 1 && (uint64_t)coff + (uint64_t)C <= e->bufs[b].C; };
+    auto tensor_ok = [&](int t, uint64_t min_bytes) { return t >= 0 && t < nt && e->tensors[t].bytes >= min_bytes; };
+    for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+        const PlanOp& op = e->ops[oi];
+        const int32_t* p = op.p;
+        switch (op.type) {
+            case OP_GEMM: {
+                const int Kc = p[2], ntaps = p[3], N = p[6], transposed = p[14];
+                ADAS_CHECK(Kc >= 8 && Kc <= (1 << 20) && N >= 1 && N <= (1 << 20) && (ntaps == 1 || ntaps == 4 || ntaps == 9), "plan %s: op %zu: bad GEMM shape", path, oi);
+                ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[11]) && p[1] >= 0 && p[12] >= 0, "plan %s: op %zu: GEMM buffer index out of range", path, oi);
+                if (!transposed) {
+                    ADAS_CHECK(view_ok(p[0], p[1], Kc) && view_ok(p[11], p[12], N), "plan %s: op %zu: GEMM channel slice exceeds its buffer", path, oi);
+                } else {
+                    const PlanBuffer &ab = e->bufs[p[0]], &ob = e->bufs[p[11]];
+                    ADAS_CHECK(p[1] == 0 && p[12] == 0 && (uint64_t)Kc <= (uint64_t)ab.rows_per_img * ab.C && (uint64_t)N <= (uint64_t)ob.rows_per_img * ob.C,
+                               "plan %s: op %zu: FC vector exceeds its buffer", path, oi);
+                }
+                ADAS_CHECK(tensor_ok(p[4], (uint64_t)N * Kc * ntaps * 2) && e->tensors[p[4]].dtype == 0, "plan %s: op %zu: weight tensor missing or too small", path, oi);
+                ADAS_CHECK(p[5] < 0 || (tensor_ok(p[5], (uint64_t)N * 4) && e->tensors[p[5]].dtype == 1), "plan %s: op %zu: bias tensor missing or too small", path, oi);
+                ADAS_CHECK(p[8] < 0 || (!transposed && view_ok(p[8], p[9], N) && e->bufs[p[8]].dtype == 0), "plan %s: op %zu: residual slice exceeds its buffer", path, oi);
+                ADAS_CHECK(p[15] >= 0 && p[15] <= 256 && p[17] >= 0 && p[17] <= 4, "plan %s: op %zu: bad forced tile shape", path, oi);
+                break;
+            }
+            case OP_IM2COL:
+                ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[7]) && view_ok(p[0], p[1], p[2]) && e->bufs[p[0]].H > 0 && e->bufs[p[7]].H > 0 && p[3] >= 1 && p[3] <= 7 && p[4] >= 1 && p[4] <= 7 &&
+                           p[5] >= 1 && p[5] <= 4 && p[6] >= 0 && p[6] <= 3 && (uint64_t)p[2] * p[3] * p[4] <= e->bufs[p[7]].C,
+                           "plan %s: op %zu: bad im2col", path, oi);
+                break;
+            case OP_MAXPOOL:
+                ADAS_CHECK(view_ok(p[0], p[1], p[2]) && view_ok(p[6], p[7], p[2]) && e->bufs[p[0]].H > 0 && e->bufs[p[6]].H > 0 && p[3] >= 1 && p[3] <= 7 && p[4] >= 1 && p[4] <= 4 && p[5] >= 0 && p[5] <= 3,
+                           "plan %s: op %zu: bad maxpool", path, oi);
+                break;
+            case OP_UPSAMPLE2X:
+                ADAS_CHECK(view_ok(p[0], p[1], p[2]) && view_ok(p[3], p[4], p[2]) && e->bufs[p[0]].H > 0 && e->bufs[p[3]].H == 2 * e->bufs[p[0]].H && e->bufs[p[3]].W == 2 * e->bufs[p[0]].W,
+                           "plan %s: op %zu: bad upsample", path, oi);
+                break;
+            case OP_STEMPACK:
+                ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[1]) && e->bufs[p[0]].H > 0 && e->bufs[p[1]].H > 0 && e->bufs[p[0]].C == 4 && e->bufs[p[1]].C == 64, "plan %s: op %zu: bad stem re-layout", path, oi);
+                break;
+            case OP_LAYERNORM: {
+                ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[4]) && p[1] >= 1 && p[5] >= 1 && p[5] <= p[1], "plan %s: op %zu: bad layernorm", path, oi);
+                const PlanBuffer &ib = e->bufs[p[0]], &ob = e->bufs[p[4]];
+                ADAS_CHECK((uint64_t)p[1] <= (uint64_t)ib.rows_per_img * ib.C && (uint64_t)p[1] <= (uint64_t)ob.rows_per_img * ob.C && tensor_ok(p[2], (uint64_t)p[1] * 4) && tensor_ok(p[3], (uint64_t)p[1] * 4),
+                           "plan %s: op %zu: layernorm vector exceeds its buffers", path, oi);
+                break;
+            }
+            default:
+                ADAS_CHECK(false, "plan %s: op %zu has unknown type %u", path, oi, op.type);
+        }
+    }
+    for (size_t i = 0; i < e->outs.size(); ++i) {
+        const PlanOutput& o = e->outs[i];
+        ADAS_CHECK(buf_ok((int)o.buffer) && (uint64_t)o.coff + o.C <= (uint64_t)e->bufs[o.buffer].C * (e->bufs[o.buffer].H > 0 ? 1u : e->bufs[o.buffer].rows_per_img) && o.C >= 1,
+                   "plan %s: output %zu exceeds its buffer", path, i);
+    }
+    if (h.model_kind == ADAS_MODEL_UFLDV2) {
+        const uint64_t ngr = h.meta[0], ncr = h.meta[1], ngc = h.meta[2], ncc = h.meta[3], nl = h.meta[4];
+        ADAS_CHECK(nl == 4 && ngr >= 2 && ncr >= 1 && ngc >= 2 && ncc >= 1 && ngr <= 1024 && ngc <= 1024 && ncr <= 1024 && ncc <= 1024, "plan %s: bad UFLD head dimensions", path);
+        ADAS_CHECK(h.meta[5] == ngr * ncr * nl + ngc * ncc * nl + 2 * ncr * nl + 2 * ncc * nl, "plan %s: UFLD total_dim does not match the head dimensions", path);
+        const UfldDataset* ds = ufld_dataset(h);
+        ADAS_CHECK(ds != nullptr, "plan %s: unknown UFLD dataset id %u (0 = CULane, 1 = TuSimple; CurveLanes is rejected like the reference does)", path, h.meta[6]);
+        ADAS_CHECK((int)ngr == ds->ngr && (int)ncr == ds->ncr && (int)ngc == ds->ngc && (int)ncc == ds->ncc && (int)h.in_h == ds->in_h && (int)h.in_w == ds->in_w,
+                   "plan %s: head %llux%llu / %llux%llu at %ux%u is not the %s geometry its header names", path, (unsigned long long)ngr, (unsigned long long)ncr,
+                   (unsigned long long)ngc, (unsigned long long)ncc, h.in_h, h.in_w, ds->name);
+    } else {
+        ADAS_CHECK(h.model_kind == ADAS_MODEL_YOLOV8 || h.model_kind == ADAS_MODEL_YOLOV5, "plan %s: unknown model kind %u", path, h.model_kind);
+        ADAS_CHECK(h.meta[0] >= 1 && h.meta[0] <= 1024 && h.meta[1] >= 1 && h.meta[1] <= (1u << 22), "plan %s: bad class / anchor counts", path);
+    }
+    return 0;
+}
+
 int adas_engine_create(const char* plan_path, int device, int max_batch, int conv_impl, adas_engine** out) {
     ADAS_CHECK(out != nullptr && plan_path != nullptr, "adas_engine_create: null argument");
     *out = nullptr;
@@ -601,12 +708,16 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     e->autotune = !(at && at[0] == '0');
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;
     if (!ok) { fclose(f); ADAS_CHECK(false, "Parameters must be a .b200w plan file (bad magic/version): %s", plan_path); }
+    if (e->hdr.n_buffers > 65536 || e->hdr.n_ops > 65536 || e->hdr.n_tensors > 65536 || e->hdr.n_outputs > 64) { fclose(f); ADAS_CHECK(false, "plan %s: implausible record counts", plan_path); }
     e->bufs.resize(e->hdr.n_buffers); e->ops.resize(e->hdr.n_ops); e->tensors.resize(e->hdr.n_tensors); e->outs.resize(e->hdr.n_outputs);
     ok = fread(e->bufs.data(), sizeof(PlanBuffer), e->bufs.size(), f) == e->bufs.size() &&
          fread(e->ops.data(), sizeof(PlanOp), e->ops.size(), f) == e->ops.size() &&
          fread(e->tensors.data(), sizeof(PlanTensor), e->tensors.size(), f) == e->tensors.size() &&
          fread(e->outs.data(), sizeof(PlanOutput), e->outs.size(), f) == e->outs.size();
     if (!ok) { fclose(f); ADAS_CHECK(false, "truncated plan file %s", plan_path); }
+    fseek(f, 0, SEEK_END);
+    const uint64_t file_bytes = (uint64_t)ftell(f);
+    if (validate_plan(e.get(), file_bytes, plan_path)) { fclose(f); return 1; }
     std::vector<uint8_t> blob(e->hdr.blob_bytes);
     fseek(f, (long)e->hdr.blob_offset, SEEK_SET);
     ok = fread(blob.data(), 1, blob.size(), f) == blob.size();
@@ -640,12 +751,13 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
         ADAS_CUDA(cudaMemcpy(e->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
         const int ncr = (int)e->hdr.meta[1], ncc = (int)e->hdr.meta[3];
         e->ufld_max_pts = ncr > ncc ? ncr : ncc;
-        // CULane anchors (ModelConfig.init_culane_config, ultrafastLaneDetectorV2.py:47-55): np.linspace semantics
+        // anchors of the plan's dataset (ModelConfig, ultrafastLaneDetectorV2.py:31-55) with np.linspace semantics:
+        // start + i*step, step = (stop-start)/(n-1), last element forced to stop; TuSimple divides the row anchors by 720 afterwards
+        const UfldDataset* ds = ufld_dataset(e->hdr);
+        e->ufld_crop = ds->crop;
         std::vector<double> ra(ncr), ca(ncc);
-        // np.linspace(start, stop, n): start + i*step with step = (stop-start)/(n-1), last element forced to stop
-        const double r0 = 0.42, r1 = 1.0, c0 = 0.0, c1 = 1.0;
-        for (int i = 0; i < ncr; ++i) ra[i] = (i == ncr - 1) ? r1 : r0 + (double)i * ((r1 - r0) / (double)(ncr - 1));
-        for (int i = 0; i < ncc; ++i) ca[i] = (i == ncc - 1) ? c1 : c0 + (double)i * ((c1 - c0) / (double)(ncc - 1));
+        for (int i = 0; i < ncr; ++i) ra[i] = ((i == ncr - 1) ? ds->r1 : ds->r0 + (double)i * ((ds->r1 - ds->r0) / (double)(ncr - 1))) / ds->rdiv;
+        for (int i = 0; i < ncc; ++i) ca[i] = (i == ncc - 1) ? ds->c1 : ds->c0 + (double)i * ((ds->c1 - ds->c0) / (double)(ncc - 1));
         ADAS_CUDA(cudaMalloc(&e->d_row_anchor, ncr * 8));
         ADAS_CUDA(cudaMalloc(&e->d_col_anchor, ncc * 8));
         ADAS_CUDA(cudaMemcpy(e->d_row_anchor, ra.data(), ncr * 8, cudaMemcpyHostToDevice));
@@ -841,7 +953,7 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
     tr.mark("h2d");
     const int in_h = (int)e->hdr.in_h, in_w = (int)e->hdr.in_w;
-    const int resize_h = (int)((double)in_h / 0.6);   // int(self.input_height / cfg.crop_ratio), CULane crop_ratio 0.6
+    const int resize_h = (int)((double)in_h / e->ufld_crop);   // int(self.input_height / cfg.crop_ratio)
     if (launch_ufld_pre(dfr, batch, H, W, in_h, in_w, resize_h, e->d_lut, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr,
                         e->stream)) return 1;
     tr.mark("pre");
@@ -899,7 +1011,7 @@ int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames
     {
         adas_engine* u = ufld;
         const int in_h = (int)u->hdr.in_h, in_w = (int)u->hdr.in_w;
-        const int resize_h = (int)((double)in_h / 0.6);
+        const int resize_h = (int)((double)in_h / u->ufld_crop);
         if (launch_ufld_pre(frames, batch, H, W, in_h, in_w, resize_h, u->d_lut, static_cast<__half*>(u->dbufs[0].ptr), (int)u->bufs[0].C, nullptr,
                             u->stream)) return 1;
     }

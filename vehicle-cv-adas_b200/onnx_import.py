@@ -21,7 +21,6 @@ import hashlib
 import os
 import re
 import struct
-import tempfile
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -388,7 +387,8 @@ def build_plan(model: OnnxModel, spec: Optional[ModelSpec] = None) -> "plan.Plan
     if spec.kind == "yolov5":
         return plan.build_yolov5(w, spec.scale, nc=spec.nc, in_h=spec.in_h, in_w=spec.in_w)
     if spec.kind == "ufldv2":
-        cfg = dict(plan.UFLD_CULANE)
+        # the dataset follows from the input binding (ModelConfig: CULane 320x1600, TuSimple 320x800); the engine rejects any other
+        cfg = dict(plan.UFLD_TUSIMPLE if (spec.in_h, spec.in_w) == (320, 800) else plan.UFLD_CULANE)
         cfg["in_h"], cfg["in_w"] = spec.in_h, spec.in_w
         return plan.build_ufldv2(w, spec.scale, cfg)
     raise Exception(f"unsupported model kind {spec.kind}")
@@ -402,8 +402,7 @@ def plan_from_onnx(onnx_path: str, out_path: Optional[str] = None) -> str:
     st = os.stat(onnx_path)
     if out_path is None:
         tag = hashlib.sha1(f"{os.path.abspath(onnx_path)}:{st.st_size}:{st.st_mtime_ns}:{plan.PLAN_VERSION}".encode()).hexdigest()[:16]
-        cache = os.environ.get("ADAS_B200_PLAN_CACHE", os.path.join(tempfile.gettempdir(), "adas_b200_plans"))
-        os.makedirs(cache, exist_ok=True)
+        cache = plan.cache_dir()
         out_path = os.path.join(cache, f"{os.path.splitext(os.path.basename(onnx_path))[0]}-{tag}.b200w")
     if os.path.isfile(out_path) and os.path.getmtime(out_path) >= st.st_mtime:
         return out_path

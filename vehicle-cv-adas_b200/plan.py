@@ -36,6 +36,19 @@ ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 PLAN_VERSION = 1
 
 
+def cache_dir() -> str:
+    """Directory for converted / synthetic plan files: $ADAS_B200_PLAN_CACHE, else ~/.cache/adas_b200 -- created 0700 and refused if it
+    belongs to another user or is writable by others (a plan is trusted input to the engine; the reference writes its .trt next to
+    the .onnx the user named, convertOnnxToTensorRT.py)."""
+    d = os.environ.get("ADAS_B200_PLAN_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "adas_b200")
+    os.makedirs(d, mode=0o700, exist_ok=True)
+    st = os.stat(d)
+    if hasattr(os, "getuid") and (st.st_uid != os.getuid() or (st.st_mode & 0o022)):
+        raise Exception(f"plan cache {d} is not a private directory of this user (owner {st.st_uid}, mode {oct(st.st_mode & 0o777)})")
+    return d
+
+
+
 # ---------------------------------------------------------------------------------------------
 # weights: real state_dict or seeded synthetic
 # ---------------------------------------------------------------------------------------------
@@ -519,11 +532,19 @@ def build_yolov5(weights: Weights, scale: str = "n", nc: int = 80, in_h: int = 6
 # ---------------------------------------------------------------------------------------------
 # UFLDv2 (model_culane.parsingNet, backbone.resnet 18/34)
 # ---------------------------------------------------------------------------------------------
-UFLD_CULANE = dict(num_grid_row=200, num_cls_row=72, num_grid_col=100, num_cls_col=81, num_lanes=4, in_h=320, in_w=1600, fc_norm=True)
+# dataset geometries: ModelConfig (ultrafastLaneDetectorV2.py:31-55) + exportLib/ultrafastLaneV2/configs/{culane,tusimple}_res*.py
+# (`dataset` is the id stored in the plan header, meta[6]; the engine derives crop ratio and anchors from it)
+UFLD_CULANE = dict(num_grid_row=200, num_cls_row=72, num_grid_col=100, num_cls_col=81, num_lanes=4, in_h=320, in_w=1600, fc_norm=True,
+                   dataset=0, crop_ratio=0.6)
+UFLD_TUSIMPLE = dict(num_grid_row=100, num_cls_row=56, num_grid_col=100, num_cls_col=41, num_lanes=4, in_h=320, in_w=800, fc_norm=False,
+                     dataset=1, crop_ratio=0.8)
+UFLD_DATASETS = {"culane": UFLD_CULANE, "tusimple": UFLD_TUSIMPLE}
 BN_EPS_TV = 1e-5
 
 
-def build_ufldv2(weights: Weights, backbone: str = "34", cfg: dict = UFLD_CULANE) -> PlanBuilder:
+def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> PlanBuilder:
+    if isinstance(cfg, str):
+        cfg = UFLD_DATASETS[cfg]
     blocks = {"18": [2, 2, 2, 2], "34": [3, 4, 6, 3]}[backbone]
     in_h, in_w = cfg["in_h"], cfg["in_w"]
     pb = PlanBuilder(MODEL_UFLDV2, 3, in_h, in_w)
@@ -583,12 +604,14 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg: dict = UFLD_CULANE
         feat_buf = ln_buf
         fc_in_K = slab
     else:
-        # without fc_norm the FC reads the padded slab directly: view it as one row per image
-        raise NotImplementedError("fc_norm=False plans are not packed yet")
+        # fc_norm=False (TuSimple configs): cls.0 is Identity; the FC reads the pool conv's padded slab directly, one row per image
+        # (its halo entries are structural zeros and meet zero weight columns)
+        fc_in_K = slab
     h_buf = pb.new_dense(1, mid)
     pb.fc(feat_buf, fc_in_K, w1p, b1, ACT_RELU, h_buf)
     o_buf = pb.new_dense(1, total_dim, f32=True)
     pb.fc(h_buf, mid, w2, b2, ACT_NONE, o_buf)
     pb.outputs.append((o_buf, 0, total_dim, 0))
     pb.meta[0:6] = [ngr, ncr, ngc, ncc, nl, total_dim]
+    pb.meta[6] = int(cfg.get("dataset", 0))
     return pb

@@ -30,8 +30,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GFLOP_YOLOV8L = 165.1
-GFLOP_UFLD34 = 75.15
 FRAME_H, FRAME_W = 720, 1280
 BOX_SCORE, NMS_IOU, MAX_DET = 0.4, 0.45, 300
 
@@ -311,7 +309,10 @@ def run_b200(args):
         ms_u, n_u = pipe.ufld.time_ops(B, 1 << 1, 5)
         ms_all_y, _ = pipe.yolo.time_ops(B, 0xFFFFFFFF, 5)
         ms_all_u, _ = pipe.ufld.time_ops(B, 0xFFFFFFFF, 5)
-        gflop_step = (GFLOP_YOLOV8L + GFLOP_UFLD34) * B
+        # FLOPs of the launches that are timed here: the stem convs run in stem_conv.cu (warp MMA), not in the tcgen05 GEMM launches
+        gf_y = (plans["yolov8"][2].flops_per_img - plans["yolov8"][2].stem_flops_per_img) / 1e9
+        gf_u = (plans["ufldv2"][2].flops_per_img - plans["ufldv2"][2].stem_flops_per_img) / 1e9
+        gflop_step = (gf_y + gf_u) * B
         achieved = gflop_step / (ms_y + ms_u)          # GFLOP / ms == TFLOP/s
         # DRAM bytes per GEMM launch: measured by ncu over whole steps of THIS command (bench.py --profile-steps, caches not flushed
         # between launches); tools/traffic_report.py turns the capture into the JSON read here.  null if the capture is absent.
@@ -356,7 +357,7 @@ def run_b200(args):
             # BASELINE configs[1] / configs[2]: the two conv stacks alone at batch 32 (GEMM launches of one pass, timed like `roofline`)
             pipe.close()
             other = {}
-            for name, key, gf in (("yolov8l_b32 (configs[1])", "yolov8", GFLOP_YOLOV8L), ("ufldv2_res34_b32 (configs[2])", "ufldv2", GFLOP_UFLD34)):
+            for name, key, gf in (("yolov8l_b32 (configs[1])", "yolov8", gf_y), ("ufldv2_res34_b32 (configs[2])", "ufldv2", gf_u)):
                 eng = _capi.Engine(plans[key][0], local, max_batch=32)
                 ms_g, n_g = eng.time_ops(32, 1 << 1, 3)
                 ms_a, _ = eng.time_ops(32, 0xFFFFFFFF, 3)

@@ -170,6 +170,40 @@ def test_stem_convs(tmp_path, impl):
         assert err < 4e-3, (k, err)
 
 
+@pytest.mark.parametrize("k,pad,cout,act", [(3, 1, 64, 1), (3, 1, 16, 1), (3, 1, 48, 0), (6, 2, 16, 1), (6, 2, 32, 2), (7, 3, 64, 2)])
+def test_stem_conv_direct(tmp_path, k, pad, cout, act):
+    """stem_conv.cu: k x k stride-2 conv straight from the C=4 image (YOLOv8 3x3, YOLOv5 6x6 p2, ResNet 7x7 p3) -- borders that reach
+    beyond the one-pixel halo, widths that are not a multiple of the 16-pixel warp tile, batch > 1, every supported Cout."""
+    rng = np.random.default_rng(100 + k + cout)
+    for (B, H, W) in ((2, 64, 96), (3, 36, 50), (1, 20, 34)):
+        pb = plan.PlanBuilder(plan.MODEL_YOLOV8, 3, H, W)
+        w = (rng.standard_normal((cout, 3, k, k)) * np.sqrt(2.0 / (3 * k * k))).astype(np.float32)
+        b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+        out = pb.conv(pb.image, w, b, k, 2, act, pad=pad)
+        assert [op[0] for op in pb.ops] == [plan.OP_STEMCONV]
+        path = str(tmp_path / f"stemd_{k}_{cout}_{H}.b200w")
+        pb.write(path)
+        eng = _capi.Engine(path, 0, max_batch=B)
+        x = rng.standard_normal((B, 3, H, W)).astype(np.float32)
+        eng.write_buffer(pb.image.buf, to_padded(x, 4))
+        for _ in range(3):
+            eng.run(B)
+        Ho, Wo = (H + 2 * pad - k) // 2 + 1, (W + 2 * pad - k) // 2 + 1
+        got_buf = eng.read_buffer(out.buf, B)
+        got = from_padded(got_buf, B, Ho, Wo, 0, cout)
+        ref = F.conv2d(torch.from_numpy(x).half().float(), torch.from_numpy(w).half().float(), torch.from_numpy(b), stride=2, padding=pad)
+        ref = {0: lambda t: t, 1: F.silu, 2: F.relu}[act](ref).numpy()
+        err = float(np.abs(got - ref).max()) / max(1.0, float(np.abs(ref).max()))
+        assert err < 2e-3, (k, cout, H, err)
+        assert halo_is_zero(got_buf, B, Ho, Wo)
+        # frame 0 alone gives the same bits (batch invariance)
+        eng1 = _capi.Engine(path, 0, max_batch=1)
+        eng1.write_buffer(pb.image.buf, to_padded(x[:1], 4))
+        eng1.run(1)
+        assert np.array_equal(eng1.read_buffer(out.buf, 1), got_buf[:got_buf.shape[0] // B])
+        eng1.close(); eng.close()
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 def test_stem_repack_7x7s2(tmp_path, impl):
     """UFLD/ResNet stem without a patch matrix: stempack re-layout + 4 vertical GEMM taps == conv2d(7, stride 2, pad 3)."""

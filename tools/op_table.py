@@ -11,7 +11,7 @@ path, sd, pb = cached_plan(kind, **kw)
 eng = _capi.Engine(path, 0, max_batch=B)
 eng.run(B)
 n = eng.num_steps(B)
-names = {1: "gemm", 2: "im2col", 3: "maxpool", 4: "upsample", 5: "layernorm", 6: "stempack", 31: "(folded)"}
+names = {1: "gemm", 2: "im2col", 3: "maxpool", 4: "upsample", 5: "layernorm", 6: "stempack", 7: "stemconv", 31: "(folded)"}
 tot = 0.0; tot_g = 0.0; rows = []
 for i in range(n):
     ms, t, d = eng.time_step(B, i, iters)
@@ -25,7 +25,7 @@ for i in range(n):
             tf = f"{2.0 * M * N * K / ms / 1e9:7.1f} TF(incl halo)"
     rows.append((ms, i, names.get(t, str(t)), d, tf))
     print(f"{i:3d} {names.get(t, str(t)):9s} {ms * 1e3:8.1f} us {tf} {d}", flush=True)
-flops = pb.flops_per_img * B
+flops = (pb.flops_per_img - pb.stem_flops_per_img) * B      # the stem conv is not a GEMM launch
 print(f"TOTAL {kind} b{B}: sum of isolated launches {tot * 1e3:.1f} us (gemm {tot_g * 1e3:.1f} us) -> {flops / tot_g / 1e9:.1f} TFLOP/s algorithmic over GEMM time")
 ms_all, nl = eng.time_ops(B, 0xFFFFFFFF, 10)
 ms_g, ng = eng.time_ops(B, 1 << 1, 10)

@@ -106,6 +106,10 @@ int launch_fc_stream(const __half* x, int x_ld, int batch, const __half* W, int 
                      int out_f32, cudaStream_t st);
 int launch_nchw_to_padded(const float* in, int B, int C, int H, int W, __half* out, int out_ld, cudaStream_t st);
 int launch_stempack(const __half* img, int B, int H, int W, __half* q, cudaStream_t st);
+// stem_conv.cu: k x k stride-2 conv of the padded C=4 image (warp-level MMA, no patch matrix)
+int stem_conv_supported(int Cout, int k, int pad);
+int launch_stem_conv_s2(const __half* img, int B, int H, int W, const __half* wq, const float* bias, int Cout, int k, int pad, int act,
+                        __half* out, int out_ld, int Ho, int Wo, cudaStream_t st);
 int launch_zero_rows(__half* buf, int ld, int C, int row0, int nrows, cudaStream_t st);
 
 // ---- pre-processing (preprocess.cu) -----------------------------------------------------------

@@ -292,14 +292,18 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                     }
                 } else {
                     // swap-AB: rows = output features (weights stream once through the A operand), cols = batch rows
+                    // FC semantics: ONE input vector per image -- the whole per-image slab of the input buffer (a dense [1, K] row, or a
+                    // padded feature map read flat: its halo entries are zeros that meet zero weight columns)
+                    const uint64_t x_ld = (uint64_t)ab.rows_per_img * ab.C;
                     g.M = N;
-                    g.N = a_rows;
-                    BN = (a_rows + 15) / 16 * 16;
-                    ADAS_CHECK(BN <= 256, "op %zu: transposed GEMM supports at most 256 activation rows", oi);
+                    g.N = batch;
+                    BN = (batch + 15) / 16 * 16;
+                    ADAS_CHECK(BN <= 256, "op %zu: transposed GEMM supports at most 256 images per batch", oi);
+                    ADAS_CHECK((uint64_t)Kc <= x_ld && a_coff == 0 && (x_ld * 2) % 16 == 0, "op %zu: FC input vector exceeds its buffer", oi);
                     opA = wptr; a_inner = (uint64_t)Ktot; a_rows_u = (uint64_t)N; a_stride = (uint64_t)Ktot * 2;
-                    opB = aptr; b_inner = (uint64_t)Kc; b_rows_u = (uint64_t)a_rows; b_stride = (uint64_t)ab.C * 2;
-                    g.A = wptr; g.a_ld = Ktot; g.Wt = aptr; g.w_ld = (int)ab.C;
-                    g.out_ld = (int)ob.C;
+                    opB = aptr; b_inner = (uint64_t)Kc; b_rows_u = (uint64_t)batch; b_stride = x_ld * 2;
+                    g.A = wptr; g.a_ld = Ktot; g.Wt = aptr; g.w_ld = (int)x_ld;
+                    g.out_ld = (int)(ob.rows_per_img * ob.C);
                 }
                 if (p[17] > 0) g.mt_hint = p[17];       // plan-forced sub-tile count (test hook of plan.py)
                 // Fully connected layers whose weight matrix stays in L2 (FC1 of the UFLD head: 20 MB) run as a weight stream on the CUDA
@@ -434,6 +438,23 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
                 __half* out = static_cast<__half*>(e->dbufs[p[1]].ptr);
                 const int H = (int)ib.H, W = (int)ib.W;
                 prog->steps.push_back([=](cudaStream_t st) { return launch_stempack(in, batch, H, W, out, st); });
+                break;
+            }
+            case OP_STEMCONV: {
+                const PlanBuffer& ib = e->bufs[p[0]];
+                const PlanBuffer& ob = e->bufs[p[7]];
+                const int Cout = p[3], k = p[4], pad = p[5], act = p[6], out_coff = p[8];
+                ADAS_CHECK(ib.C == 4 && ib.dtype == 0 && ob.dtype == 0 && stem_conv_supported(Cout, k, pad) && out_coff % 8 == 0 && ob.C % 8 == 0, "op %zu: stem conv geometry", oi);
+                const __half* in = static_cast<const __half*>(e->dbufs[p[0]].ptr);
+                const __half* wq = static_cast<const __half*>(tensor_ptr(e, p[1]));
+                const float* bias = static_cast<const float*>(tensor_ptr(e, p[2]));
+                __half* out = static_cast<__half*>(e->dbufs[p[7]].ptr) + out_coff;
+                const int H = (int)ib.H, W = (int)ib.W, Ho = (int)ob.H, Wo = (int)ob.W, out_ld = (int)ob.C;
+                char d[128];
+                snprintf(d, sizeof(d), "stem %dx%d s2 p%d 3->%d, %dx%d -> %dx%d, warp MMA from the image", k, k, pad, Cout, H, W, Ho, Wo);
+                prog->step_desc.resize(prog->step_type.size());
+                prog->step_desc.back() = d;
+                prog->steps.push_back([=](cudaStream_t st) { return launch_stem_conv_s2(in, batch, H, W, wq, bias, Cout, k, pad, act, out, out_ld, Ho, Wo, st); });
                 break;
             }
             case OP_LAYERNORM: {
@@ -608,8 +629,7 @@ static int validate_plan(const adas_engine* e, uint64_t file_bytes, const char* 
     ADAS_CHECK(h.blob_offset >= rec_bytes && h.blob_offset <= file_bytes && h.blob_bytes <= file_bytes - h.blob_offset,
                "plan %s: weight blob [%llu, +%llu) lies outside the file (%llu bytes)", path, (unsigned long long)h.blob_offset,
                (unsigned long long)h.blob_bytes, (unsigned long long)file_bytes);
-    ADAS_CHECK(h.in_c >= 1 && h.in_c <= 4 && h.in_h >= 32 && h.in_h <= 8192 && h.in_w >= 32 && h.in_w <= 8192, "plan %s: bad input binding %ux%ux%u", path, h.in_c, h.in_h, h.in_w);
-    ADAS_CHECK(h.n_outputs >= 1, "plan %s: no outputs", path);
+    ADAS_CHECK(h.in_c >= 1 && h.in_c <= 4 && h.in_h >= 1 && h.in_h <= 8192 && h.in_w >= 1 && h.in_w <= 8192, "plan %s: bad input binding %ux%ux%u", path, h.in_c, h.in_h, h.in_w);
     const int nb = (int)h.n_buffers, nt = (int)h.n_tensors;
     for (int i = 0; i < nb; ++i) {
         const PlanBuffer& b = e->bufs[i];
@@ -660,6 +680,15 @@ static int validate_plan(const adas_engine* e, uint64_t file_bytes, const char* 
             case OP_STEMPACK:
                 ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[1]) && e->bufs[p[0]].H > 0 && e->bufs[p[1]].H > 0 && e->bufs[p[0]].C == 4 && e->bufs[p[1]].C == 64, "plan %s: op %zu: bad stem re-layout", path, oi);
                 break;
+            case OP_STEMCONV: {
+                const int Cout = p[3], k = p[4];
+                ADAS_CHECK(buf_ok(p[0]) && e->bufs[p[0]].H > 0 && e->bufs[p[0]].C == 4 && Cout >= 8 && Cout <= 64 && k >= 3 && k <= 7 && p[5] >= 0 && p[5] <= 3 &&
+                           view_ok(p[7], p[8], Cout) && e->bufs[p[7]].H > 0 && tensor_ok(p[1], (uint64_t)Cout * k * ((4 * k + 15) / 16 * 16) * 2) &&
+                           (p[2] < 0 || tensor_ok(p[2], (uint64_t)Cout * 4)) &&
+                           e->bufs[p[7]].H == (e->bufs[p[0]].H + 2 * p[5] - k) / 2 + 1 && e->bufs[p[7]].W == (e->bufs[p[0]].W + 2 * p[5] - k) / 2 + 1,
+                           "plan %s: op %zu: bad stem conv", path, oi);
+                break;
+            }
             case OP_LAYERNORM: {
                 ADAS_CHECK(buf_ok(p[0]) && buf_ok(p[4]) && p[1] >= 1 && p[5] >= 1 && p[5] <= p[1], "plan %s: op %zu: bad layernorm", path, oi);
                 const PlanBuffer &ib = e->bufs[p[0]], &ob = e->bufs[p[4]];
@@ -676,6 +705,7 @@ static int validate_plan(const adas_engine* e, uint64_t file_bytes, const char* 
         ADAS_CHECK(buf_ok((int)o.buffer) && (uint64_t)o.coff + o.C <= (uint64_t)e->bufs[o.buffer].C * (e->bufs[o.buffer].H > 0 ? 1u : e->bufs[o.buffer].rows_per_img) && o.C >= 1,
                    "plan %s: output %zu exceeds its buffer", path, i);
     }
+    if (h.n_outputs == 0) return 0;          // single-layer plans of the kernel tests: no network outputs, no head geometry
     if (h.model_kind == ADAS_MODEL_UFLDV2) {
         const uint64_t ngr = h.meta[0], ncr = h.meta[1], ngc = h.meta[2], ncc = h.meta[3], nl = h.meta[4];
         ADAS_CHECK(nl == 4 && ngr >= 2 && ncr >= 1 && ngc >= 2 && ncc >= 1 && ngr <= 1024 && ngc <= 1024 && ncr <= 1024 && ncc <= 1024, "plan %s: bad UFLD head dimensions", path);

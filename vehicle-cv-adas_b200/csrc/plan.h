@@ -49,6 +49,8 @@ enum PlanOpType : uint32_t {
     OP_MAXPOOL = 3,    // p: in_buf in_coff C k s pad out_buf out_coff
     OP_UPSAMPLE2X = 4, // p: in_buf in_coff C out_buf out_coff
     OP_STEMPACK = 6,   // p: in_buf(image, C=4) out_buf : 7x7 stride-2 stem re-layout, see elementwise.cu stempack_kernel
+    OP_STEMCONV = 7,   // p: in_buf(image, C=4) w_tensor bias_tensor Cout k pad act out_buf out_coff : k x k stride-2 stem conv, stem_conv.cu
+                       //    (weights packed [Cout][k][round_up(4k,16)])
     OP_LAYERNORM = 5,  // p: in_buf d_len gamma_tensor beta_tensor out_buf d_norm ; f0 = eps (statistics over d_norm entries; the
                        //    other d_len - d_norm slab entries are structural zeros with gamma = beta = 0)
 };

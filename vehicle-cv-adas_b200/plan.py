@@ -31,7 +31,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 MODEL_YOLOV8, MODEL_YOLOV5, MODEL_UFLDV2 = 0, 1, 2
-OP_GEMM, OP_IM2COL, OP_MAXPOOL, OP_UPSAMPLE2X, OP_LAYERNORM, OP_STEMPACK = 1, 2, 3, 4, 5, 6
+OP_GEMM, OP_IM2COL, OP_MAXPOOL, OP_UPSAMPLE2X, OP_LAYERNORM, OP_STEMPACK, OP_STEMCONV = 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 PLAN_VERSION = 1
 
@@ -193,6 +193,8 @@ class PlanBuilder:
         self.outputs: List[Tuple[int, int, int, int]] = []
         self.meta = [0] * 16
         self.flops_per_img = 0   # 2*MAC of the convs/FCs as mathematically defined (no padding waste)
+        self.stem_flops_per_img = 0   # the part of flops_per_img that runs in stem_conv.cu (mma.sync) rather than in the tcgen05 GEMM launches
+        self.stem_direct = os.environ.get("ADAS_B200_STEMCONV", "1") != "0"
         self.strided_tma = os.environ.get("ADAS_B200_STRIDED_TMA", "1") != "0"
         # buffer 0: the network input image, padded NHWC with C=4 (R,G,B,0)
         self.image = self.new_padded(in_h, in_w, 4)
@@ -242,6 +244,9 @@ class PlanBuilder:
         if out is None:
             out = self.new_padded(Ho, Wo, n_store, f32=out_f32)
         assert out.H == Ho and out.W == Wo, (out, Ho, Wo)
+        if (self.stem_direct and x.buf == self.image.buf and x.C == 4 and s == 2 and 3 <= k <= 7 and cout in (16, 32, 48, 64) and res is None
+                and not out_f32 and tile is None and out.coff % 8 == 0):
+            return self.stem_conv(x, w, b, k, pad, act, out)
         wk = np.transpose(w, (0, 2, 3, 1)).reshape(cout, k * k * cin)   # [Cout, kh, kw, Cin]
         if n_store != cout:
             wk = np.concatenate([wk, np.zeros((n_store - cout, wk.shape[1]), np.float32)], 0)
@@ -273,6 +278,20 @@ class PlanBuilder:
         self._op(OP_GEMM, [a.buf, a.coff, Kc, ntaps, w_t, bias_t, n_store, act, res_buf, res_coff, 1 if res_pre_act else 0,
                            out.buf, out.coff, 1, 0, bn, s2, mt])
         return View(out.buf, out.coff, cout, Ho, Wo)
+
+    def stem_conv(self, x: View, w: np.ndarray, b: Optional[np.ndarray], k: int, pad: int, act: int, out: View) -> View:
+        """k x k stride-2 conv of the C=4 image by stem_conv.cu (no patch matrix): weights packed [Cout][k][KR], KR = round_up(4k, 16),
+        element [dy][dx*4 + c] -- one 16-wide k-step of the warp MMA is a run of consecutive bytes of one image row.
+        `w` arrives zero-padded to 4 input channels."""
+        cout = int(w.shape[0])
+        KR = (4 * k + 15) // 16 * 16
+        wq = np.zeros((cout, k, KR), np.float32)
+        wq[:, :, :4 * k] = np.transpose(w, (0, 2, 3, 1)).reshape(cout, k, 4 * k)      # [Cout, dy, dx, c]
+        w_t = self.tensor(wq.astype(np.float16))
+        bias_t = self.tensor(b.astype(np.float32)) if b is not None else -1
+        self.stem_flops_per_img += 2 * out.H * out.W * cout * 3 * k * k
+        self._op(OP_STEMCONV, [x.buf, w_t, bias_t, cout, k, pad, act, out.buf, out.coff])
+        return View(out.buf, out.coff, cout, out.H, out.W)
 
     def stem7x7s2(self, x: View, w: np.ndarray, b: np.ndarray, act: int) -> View:
         """7x7 stride-2 pad-3 conv on the C=4 image without a patch matrix: the image is re-laid out once as
@@ -540,6 +559,7 @@ UFLD_TUSIMPLE = dict(num_grid_row=100, num_cls_row=56, num_grid_col=100, num_cls
                      dataset=1, crop_ratio=0.8)
 UFLD_DATASETS = {"culane": UFLD_CULANE, "tusimple": UFLD_TUSIMPLE}
 BN_EPS_TV = 1e-5
+UFLD_STEM_DEFAULT = "pack"
 
 
 def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> PlanBuilder:
@@ -550,7 +570,8 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
     pb = PlanBuilder(MODEL_UFLDV2, 3, in_h, in_w)
     W = weights
     w, b = W.conv_bn("model", 64, 3, 7, BN_EPS_TV, conv_key="conv1", bn_key="bn1")
-    if os.environ.get("ADAS_B200_STEMPACK", "1") != "0":
+    # stem: "pack" = re-layout pass + a 4-tap tcgen05 GEMM (stem7x7s2), "direct" = stem_conv.cu straight from the image
+    if os.environ.get("ADAS_B200_UFLD_STEM", UFLD_STEM_DEFAULT) == "pack":
         x = pb.stem7x7s2(pb.image, w, b, ACT_RELU)
     else:
         x = pb.conv(pb.image, w, b, 7, 2, ACT_RELU, pad=3)

@@ -42,7 +42,7 @@ struct StemParams {
     int act, tiles_per_row, total_tiles;
 };
 
-template <int NT, int KSR>      // NT n-tiles of 8 output channels, KSR 16-wide k-steps per filter row (1: k <= 4, 2: k <= 8)
+template <int NT>
 __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int w_ld = p.K + 8;                                         // halves
@@ -58,23 +58,10 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemPa
             reinterpret_cast<uint32_t*>(ws)[n * w_ld2 + kk] = src[i];
         }
     }
-    float bias0[NT], bias1[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        bias0[j] = p.bias ? p.bias[j * 8 + 2 * t] : 0.f;
-        bias1[j] = p.bias ? p.bias[j * 8 + 2 * t + 1] : 0.f;
-    }
     __syncthreads();
     __half* stg = stg_all + warp * 16 * STEM_STG_LD;
+    const int ksteps_row = p.KR >> 4;
     const uint32_t* img32 = reinterpret_cast<const uint32_t*>(p.img);   // one uint32 = 2 channels of a pixel
-    // k index inside a filter row: ks*16 + {2t, 2t+1} and + 8 -> pixel dx = kidx / 4, channel pair (kidx % 4) / 2
-    int dxs[KSR][2], cps[KSR][2];
-#pragma unroll
-    for (int ks = 0; ks < KSR; ++ks) {
-        const int k_lo = ks * 16 + 2 * t, k_hi = k_lo + 8;
-        dxs[ks][0] = k_lo >> 2; dxs[ks][1] = k_hi >> 2;
-        cps[ks][0] = (k_lo & 3) >> 1; cps[ks][1] = (k_hi & 3) >> 1;
-    }
     for (int tile = blockIdx.x * STEM_WARPS + warp; tile < p.total_tiles; tile += gridDim.x * STEM_WARPS) {
         const int b = tile / (p.Ho * p.tiles_per_row);
         const int r = tile - b * (p.Ho * p.tiles_per_row);
@@ -84,48 +71,38 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemPa
         for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
         // padded input coordinates of tap (dy = 0, dx = 0) for output pixel (y, x): row 2y + 1 - pad, column 2x + 1 - pad
         const int col_g = 2 * (x0 + g) + 1 - p.pad, col_g8 = col_g + 16;
-        // A fragments of one filter row (predicated at the image border); the next row is requested before this row's MMAs issue
-        auto load_row = [&](int dy, uint32_t (&a)[KSR][4]) {
+        for (int dy = 0; dy < p.k; ++dy) {
             const int row = 2 * y + 1 - p.pad + dy;
             const bool row_ok = row >= 0 && row < p.Hp;
             const size_t row_base = ((size_t)b * p.Hp + (row_ok ? row : 0)) * p.Wp;
-            auto ld = [&](int col, int cp) -> uint32_t {
-                return (row_ok && col >= 0 && col < p.Wp) ? __ldg(img32 + (row_base + col) * 2 + cp) : 0u;
-            };
-#pragma unroll
-            for (int ks = 0; ks < KSR; ++ks) {
-                a[ks][0] = ld(col_g + dxs[ks][0], cps[ks][0]);
-                a[ks][1] = ld(col_g8 + dxs[ks][0], cps[ks][0]);
-                a[ks][2] = ld(col_g + dxs[ks][1], cps[ks][1]);
-                a[ks][3] = ld(col_g8 + dxs[ks][1], cps[ks][1]);
-            }
-        };
-        uint32_t a_cur[KSR][4], a_nxt[KSR][4];
-        load_row(0, a_cur);
-        for (int dy = 0; dy < p.k; ++dy) {
-            if (dy + 1 < p.k) load_row(dy + 1, a_nxt);
-#pragma unroll
-            for (int ks = 0; ks < KSR; ++ks) {
+            for (int ks = 0; ks < ksteps_row; ++ks) {
+                // k index inside the row: ks*16 + {2t, 2t+1} and + 8 -> pixel dx = kidx / 4, channel pair (kidx % 4) / 2
+                const int k_lo = ks * 16 + 2 * t, k_hi = k_lo + 8;
+                const int dx_lo = k_lo >> 2, dx_hi = k_hi >> 2, cp_lo = (k_lo & 3) >> 1, cp_hi = (k_hi & 3) >> 1;
+                uint32_t a[4];
+                auto ld = [&](int col, int cp) -> uint32_t {
+                    return (row_ok && col >= 0 && col < p.Wp) ? __ldg(img32 + (row_base + col) * 2 + cp) : 0u;
+                };
+                a[0] = ld(col_g + dx_lo, cp_lo);
+                a[1] = ld(col_g8 + dx_lo, cp_lo);
+                a[2] = ld(col_g + dx_hi, cp_hi);
+                a[3] = ld(col_g8 + dx_hi, cp_hi);
                 const __half* wrow = ws + (size_t)g * w_ld + dy * p.KR + ks * 16 + 2 * t;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + (size_t)j * 8 * w_ld);
                     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + (size_t)j * 8 * w_ld + 8);
-                    mma_m16n8k16(acc[j], a_cur[ks], b0, b1);
+                    mma_m16n8k16(acc[j], a, b0, b1);
                 }
-            }
-#pragma unroll
-            for (int ks = 0; ks < KSR; ++ks) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) a_cur[ks][q] = a_nxt[ks][q];
             }
         }
         // epilogue: c0,c1 -> pixel g, channels j*8 + 2t, +1 ; c2,c3 -> pixel g + 8
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = j * 8 + 2 * t;
-            const __half2 lo = __floats2half2_rn(act_apply(acc[j][0] + bias0[j], p.act), act_apply(acc[j][1] + bias1[j], p.act));
-            const __half2 hi = __floats2half2_rn(act_apply(acc[j][2] + bias0[j], p.act), act_apply(acc[j][3] + bias1[j], p.act));
+            const float b0 = p.bias ? p.bias[n] : 0.f, b1 = p.bias ? p.bias[n + 1] : 0.f;
+            const __half2 lo = __floats2half2_rn(act_apply(acc[j][0] + b0, p.act), act_apply(acc[j][1] + b1, p.act));
+            const __half2 hi = __floats2half2_rn(act_apply(acc[j][2] + b0, p.act), act_apply(acc[j][3] + b1, p.act));
             *reinterpret_cast<__half2*>(stg + g * STEM_STG_LD + n) = lo;
             *reinterpret_cast<__half2*>(stg + (g + 8) * STEM_STG_LD + n) = hi;
         }
@@ -160,31 +137,17 @@ int launch_stem_conv_s2(const __half* img, int B, int H, int W, const __half* wq
     p.total_tiles = B * Ho * p.tiles_per_row;
     const int smem = Cout * (p.K + 8) * 2 + STEM_WARPS * 16 * STEM_STG_LD * 2;
     ADAS_CHECK(smem <= 48 * 1024, "stem_conv: %d bytes of shared memory", smem);
-    const int want = (p.total_tiles + STEM_WARPS - 1) / STEM_WARPS;
+    int blocks = (p.total_tiles + STEM_WARPS - 1) / STEM_WARPS;
     int n_sms = 148;
     if (v3_num_sms(&n_sms)) return 1;
-    const bool one = p.KR == 16;
-    // resident blocks only (the weight copy is per block; a warp then walks ~20-30 tiles)
-#define STEM_LAUNCH_K(NT_, KSR_)                                                                                             \
-    do {                                                                                                                     \
-        int per_sm = 1;                                                                                                      \
-        ADAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_s2_kernel<NT_, KSR_>, STEM_THREADS, smem)); \
-        const int cap = n_sms * (per_sm < 1 ? 1 : per_sm);                                                                   \
-        stem_conv_s2_kernel<NT_, KSR_><<<want < cap ? want : cap, STEM_THREADS, smem, st>>>(p);                              \
-    } while (0)
-#define STEM_LAUNCH(NT_)                                      \
-    do {                                                      \
-        if (one) STEM_LAUNCH_K(NT_, 1);                       \
-        else     STEM_LAUNCH_K(NT_, 2);                       \
-    } while (0)
+    const int cap = n_sms * 3;                      // resident blocks only: the weight copy is per block, a warp walks ~20 tiles
+    if (blocks > cap) blocks = cap;
     switch (Cout / 8) {
-        case 2: STEM_LAUNCH(2); break;
-        case 4: STEM_LAUNCH(4); break;
-        case 6: STEM_LAUNCH(6); break;
-        default: STEM_LAUNCH(8); break;
+        case 2: stem_conv_s2_kernel<2><<<blocks, STEM_THREADS, smem, st>>>(p); break;
+        case 4: stem_conv_s2_kernel<4><<<blocks, STEM_THREADS, smem, st>>>(p); break;
+        case 6: stem_conv_s2_kernel<6><<<blocks, STEM_THREADS, smem, st>>>(p); break;
+        default: stem_conv_s2_kernel<8><<<blocks, STEM_THREADS, smem, st>>>(p); break;
     }
-#undef STEM_LAUNCH
-#undef STEM_LAUNCH_K
     count_launch();
     ADAS_CUDA(cudaGetLastError());
     return 0;

@@ -156,9 +156,15 @@ __global__ void lap_kernel(const double* __restrict__ cost, const int64_t* __res
 //                det score D | det2 tlbr D2*4
 // out (int32):   m1[P] det index or -1 | m2[P] det2 index or -1 (only for stage-2 rows) | m3[U] ORIGINAL det index or -1 |
 //                free3[D] 1 = high-score detection unmatched after stages 1 and 3 (a birth candidate)
-__global__ void assoc3_kernel(const double* __restrict__ in, int32_t* __restrict__ out, double* __restrict__ cost, double* __restrict__ work_v,
-                              double* __restrict__ work_minv, int32_t* __restrict__ work_i, int32_t* __restrict__ lists) {
-    __shared__ double u[LAP_MAX_COLS / 2 + 1];
+// Host round trip: `in_host` / `out_host` / `done_host` are MAPPED pinned host buffers.  The warp pulls the inputs over the link with
+// coalesced loads into device scratch, solves, pushes the results back and then publishes `seq` in *done_host behind a system-scope
+// fence -- the host spins on that word (tracker.cu) instead of paying two copy-engine transfers and a stream synchronisation per frame.
+// Row potentials live in shared memory only up to ASSOC_SMEM_ROWS rows (1 KB): next to a conv CTA that holds ~224 KB of an SM's shared
+// memory this block still fits, so it starts at once instead of waiting for a conv CTA to retire; larger problems use global scratch.
+static constexpr int ASSOC_SMEM_ROWS = 120;
+
+__device__ void assoc3_body(const double* __restrict__ in, int32_t* __restrict__ out, double* __restrict__ cost, double* __restrict__ work_v,
+                            double* __restrict__ work_minv, int32_t* __restrict__ work_i, int32_t* __restrict__ lists, double* u) {
     const int lane = threadIdx.x;
     const int P = (int)in[0], U = (int)in[1], D = (int)in[2], D2 = (int)in[3];
     const double match_thresh = in[4];
@@ -224,8 +230,26 @@ __global__ void assoc3_kernel(const double* __restrict__ in, int32_t* __restrict
     }
 }
 
-int launch_assoc3(const double* in, int32_t* out, double* cost, double* work_v, double* work_minv, int32_t* work_i, int32_t* lists, cudaStream_t st) {
-    assoc3_kernel<<<1, 32, 0, st>>>(in, out, cost, work_v, work_minv, work_i, lists);
+__global__ void assoc3_kernel(const double* __restrict__ in_host, int n_in, double* __restrict__ in_dev, int32_t* __restrict__ out_host, int n_out,
+                              int32_t* __restrict__ out_dev, volatile int32_t* done_host, int32_t seq, double* __restrict__ cost,
+                              double* __restrict__ work_v, double* __restrict__ work_minv, int32_t* __restrict__ work_i, int32_t* __restrict__ lists,
+                              double* __restrict__ work_u) {
+    __shared__ double u_s[ASSOC_SMEM_ROWS + 1];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n_in; i += 32) in_dev[i] = in_host[i];
+    __syncwarp();
+    const int P = (int)in_dev[0], U = (int)in_dev[1];
+    assoc3_body(in_dev, out_dev, cost, work_v, work_minv, work_i, lists, (P <= ASSOC_SMEM_ROWS && U <= ASSOC_SMEM_ROWS) ? u_s : work_u);
+    __syncwarp();
+    for (int i = lane; i < n_out; i += 32) out_host[i] = out_dev[i];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *done_host = seq;
+}
+
+int launch_assoc3(const double* in_host, int n_in, double* in_dev, int32_t* out_host, int n_out, int32_t* out_dev, int32_t* done_host, int32_t seq,
+                  double* cost, double* work_v, double* work_minv, int32_t* work_i, int32_t* lists, double* work_u, cudaStream_t st) {
+    assoc3_kernel<<<1, 32, 0, st>>>(in_host, n_in, in_dev, out_host, n_out, out_dev, done_host, seq, cost, work_v, work_minv, work_i, lists, work_u);
     count_launch();
     ADAS_CUDA(cudaGetLastError());
     return 0;

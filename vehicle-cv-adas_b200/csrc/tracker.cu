@@ -21,7 +21,8 @@ int launch_lap(int problems, const double* cost, const int64_t* cost_off, const 
                const double* thresh, int32_t* x, const int32_t* x_off, int32_t* y, const int32_t* y_off, double* work_v,
                double* work_minv, int32_t* work_i, cudaStream_t st);
 int lap_max_cols();
-int launch_assoc3(const double* in, int32_t* out, double* cost, double* work_v, double* work_minv, int32_t* work_i, int32_t* lists, cudaStream_t st);
+int launch_assoc3(const double* in_host, int n_in, double* in_dev, int32_t* out_host, int n_out, int32_t* out_dev, int32_t* done_host, int32_t seq,
+                  double* cost, double* work_v, double* work_minv, int32_t* work_i, int32_t* lists, double* work_u, cudaStream_t st);
 
 enum { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
 static std::atomic<int> g_track_count{0};          // BaseTrack._count: process-global (base_track.py:12,33-36)
@@ -134,7 +135,10 @@ struct adas_tracker {
     std::vector<double> ha, hb, hs;
     std::vector<int32_t> hx, hy;
     // fused three-stage association (one launch + one synchronisation per frame)
-    double* h3_in = nullptr; int32_t* h3_out = nullptr;      // pinned
+    double* h3_in = nullptr; int32_t* h3_out = nullptr;      // pinned + mapped: the association kernel reads / writes them over the link
+    double* h3_in_dev = nullptr; int32_t* h3_out_dev = nullptr;   // their device-side addresses
+    int32_t* h_done = nullptr; int32_t* h_done_dev = nullptr; int32_t seq = 0;   // completion word the host spins on
+    double* d_u = nullptr;                                    // row potentials of problems beyond the kernel's shared-memory budget
     double* d3_in = nullptr; int32_t* d3_out = nullptr; double* d3_cost = nullptr; int32_t* d3_lists = nullptr;
     size_t cap3_in = 0, cap3_out = 0, cap3_cost = 0, cap3_lists = 0;
 };
@@ -151,6 +155,10 @@ static int ensure_scratch(adas_tracker* t, size_t nb, size_t nc) {
         const size_t wc = (size_t)lap_max_cols() + 1;
         ADAS_CUDA(cudaMalloc(&t->d_th, 8)); ADAS_CUDA(cudaMalloc(&t->d_v, wc * 8)); ADAS_CUDA(cudaMalloc(&t->d_mv, wc * 8));
         ADAS_CUDA(cudaMalloc(&t->d_wi, wc * 12)); ADAS_CUDA(cudaMalloc(&t->d_meta, 32)); ADAS_CUDA(cudaMalloc(&t->d_co, 16));
+        ADAS_CUDA(cudaMalloc(&t->d_u, wc * 8));
+        ADAS_CUDA(cudaHostAlloc(&t->h_done, 64, cudaHostAllocMapped));
+        *t->h_done = 0;
+        ADAS_CUDA(cudaHostGetDevicePointer(&t->h_done_dev, t->h_done, 0));
     }
     if (nb > t->cap_boxes || nc > t->cap_cost) {
         cudaFree(t->d_a); cudaFree(t->d_b); cudaFree(t->d_s); cudaFree(t->d_c); cudaFree(t->d_x); cudaFree(t->d_y);
@@ -219,14 +227,16 @@ static int assoc3_prepare(adas_tracker* t, int P, int U, int D, int D2) {
         if (t->h3_in) cudaFreeHost(t->h3_in);
         cudaFree(t->d3_in);
         t->cap3_in = std::max<size_t>(4096, n_in * 2);
-        ADAS_CUDA(cudaHostAlloc(&t->h3_in, t->cap3_in * 8, cudaHostAllocDefault));
+        ADAS_CUDA(cudaHostAlloc(&t->h3_in, t->cap3_in * 8, cudaHostAllocMapped));
+        ADAS_CUDA(cudaHostGetDevicePointer(&t->h3_in_dev, t->h3_in, 0));
         ADAS_CUDA(cudaMalloc(&t->d3_in, t->cap3_in * 8));
     }
     if (n_out > t->cap3_out) {
         if (t->h3_out) cudaFreeHost(t->h3_out);
         cudaFree(t->d3_out);
         t->cap3_out = std::max<size_t>(4096, n_out * 2);
-        ADAS_CUDA(cudaHostAlloc(&t->h3_out, t->cap3_out * 4, cudaHostAllocDefault));
+        ADAS_CUDA(cudaHostAlloc(&t->h3_out, t->cap3_out * 4, cudaHostAllocMapped));
+        ADAS_CUDA(cudaHostGetDevicePointer(&t->h3_out_dev, t->h3_out, 0));
         ADAS_CUDA(cudaMalloc(&t->d3_out, t->cap3_out * 4));
     }
     if (n_cost > t->cap3_cost) { cudaFree(t->d3_cost); t->cap3_cost = std::max<size_t>(65536, n_cost * 2); ADAS_CUDA(cudaMalloc(&t->d3_cost, t->cap3_cost * 8)); }
@@ -234,7 +244,7 @@ static int assoc3_prepare(adas_tracker* t, int P, int U, int D, int D2) {
     return 0;
 }
 
-// the three association stages of one frame: one upload, one launch (track.cu assoc3_kernel), one download, one synchronisation
+// the three association stages of one frame: one launch (track.cu assoc3_kernel) that reads and writes mapped host memory
 static int assoc3_run(adas_tracker* t, const std::vector<TrackP>& pool, const std::vector<TrackP>& unconf, const std::vector<TrackP>& dets,
                       const std::vector<TrackP>& dets2, bool need_dev, std::vector<int32_t>* m1, std::vector<int32_t>* m2, std::vector<int32_t>* m3,
                       std::vector<int32_t>* free3) {
@@ -255,10 +265,27 @@ static int assoc3_run(adas_tracker* t, const std::vector<TrackP>& pool, const st
     for (int j = 0; j < D; ++j) *q++ = dets[j]->score;
     for (int j = 0; j < D2; ++j, q += 4) dets2[j]->tlbr(q);
     const size_t n_in = (size_t)(q - h), n_out = (size_t)2 * P + U + D;
-    ADAS_CUDA(cudaMemcpyAsync(t->d3_in, h, n_in * 8, cudaMemcpyHostToDevice, t->st));
-    if (launch_assoc3(t->d3_in, t->d3_out, t->d3_cost, t->d_v, t->d_mv, t->d_wi, t->d3_lists, t->st)) return 1;
-    ADAS_CUDA(cudaMemcpyAsync(t->h3_out, t->d3_out, n_out * 4, cudaMemcpyDeviceToHost, t->st));
-    ADAS_CUDA(cudaStreamSynchronize(t->st));
+    // one launch, no copies, no stream synchronisation: the kernel pulls `h` and pushes the result through mapped host memory and
+    // publishes this frame's sequence number last; the host spins on it (and asks the stream now and then, so that a failed launch
+    // or a device fault ends the wait with an error instead of a hang)
+    const int32_t seq = ++t->seq;
+    if (launch_assoc3(t->h3_in_dev, (int)n_in, t->d3_in, t->h3_out_dev, (int)n_out, t->d3_out, t->h_done_dev, seq, t->d3_cost, t->d_v, t->d_mv, t->d_wi,
+                      t->d3_lists, t->d_u, t->st)) return 1;
+    {
+        volatile int32_t* done = t->h_done;
+        uint32_t spins = 0;
+        while (*done != seq) {
+            if ((++spins & 0xfffu) == 0) {
+                const cudaError_t q = cudaStreamQuery(t->st);
+                if (q == cudaSuccess) { ADAS_CHECK(*done == seq, "association kernel finished without publishing its result"); break; }
+                ADAS_CHECK(q == cudaErrorNotReady, "association kernel failed: %s", cudaGetErrorString(q));
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     const int32_t* o = t->h3_out;
     for (int i = 0; i < P; ++i) (*m1)[i] = o[i];
     for (int i = 0; i < P; ++i) (*m2)[i] = o[P + i];
@@ -286,6 +313,8 @@ int adas_tracker_destroy(adas_tracker* t) {
     cudaFree(t->d_mv); cudaFree(t->d_wi); cudaFree(t->d_meta); cudaFree(t->d_co);
     if (t->h3_in) cudaFreeHost(t->h3_in);
     if (t->h3_out) cudaFreeHost(t->h3_out);
+    if (t->h_done) cudaFreeHost(t->h_done);
+    cudaFree(t->d_u);
     cudaFree(t->d3_in); cudaFree(t->d3_out); cudaFree(t->d3_cost); cudaFree(t->d3_lists);
     if (t->st) cudaStreamDestroy(t->st);
     delete t;

@@ -341,6 +341,9 @@ def run_b200(args):
                     "note": "adas_b200.pipeline.AdasPipeline.step_pipelined: pinned host batch -> device staging (side stream), both detectors, tracker; results on the host every step"},
             "gpu_launches": int(launches),
             "host_tracker_ms_per_step": round(1e3 * getattr(pipe, "track_seconds", 0.0) / max(1, getattr(pipe, "track_batches", 1)), 3),
+            "host_tracker_breakdown_ms_per_step": (lambda st, nb: {"library_total": round(st["total_ms"] / nb, 3), "association_round_trips": round(st["wait_ms"] / nb, 3),
+                                                                   "association_launches_per_step": round(st["launches"] / nb, 2)})(
+                pipe.tracker._nt.stats(), max(1, getattr(pipe, "track_batches", 1))),
             "tracks_alive": len(pipe.tracker.tracked_stracks),
             "gather": ({"per_step": True, "nccl_ranks": comm.info()[0], "all_gathers": comm.info()[1], "bytes_per_rank_per_step": int(rec.nbytes)} if comm is not None else None),
             "clocks": clocks, "clocks_e2e": clocks_e2e,

@@ -197,6 +197,9 @@ int adas_tracker_update_batch(adas_tracker* t, int n_frames, const int32_t* coun
                               const double* scores, const int32_t* class_ids, int max_out, adas_track* out, int32_t* n_out);
 int adas_tracker_get(adas_tracker* t, int which /* 0 tracked, 1 lost, 2 removed */, int max_out, adas_track* out, int* n_out);
 int adas_tracker_count(void);    /* BaseTrack._count */
+/* Wall-clock accounting of adas_tracker_update_batch since the tracker was created: out4 = {frames, total ms, ms spent between the
+ * association launch and its result (the device round trip), association launches}.  Diagnostic; no reference counterpart. */
+int adas_tracker_stats(adas_tracker* t, double* out4);
 
 /* ---- test hooks (no reference counterpart): raw access to the plan's activation buffers so single kernels can be
  * parity-tested.  Buffers are [batch * rows_per_img, C] matrices (fp16 or fp32) as described in csrc/plan.h. */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
     "adas_comm_unique_id", "adas_comm_create", "adas_comm_destroy", "adas_comm_all_gather", "adas_comm_sync", "adas_comm_read", "adas_comm_info",
-    "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_update_batch", "adas_tracker_get", "adas_tracker_count",
+    "adas_tracker_create", "adas_tracker_destroy", "adas_tracker_reset", "adas_tracker_update", "adas_tracker_update_batch", "adas_tracker_get", "adas_tracker_count", "adas_tracker_stats",
 ]
 
 
@@ -102,6 +102,12 @@ class NativeTracker:
         check(lib().adas_tracker_update(self._h, int(b.shape[0]), _p(b, C.c_double), _p(s, C.c_double), _p(c, C.c_int32), self.MAX_OUT,
                                         self._out.ctypes.data_as(C.c_void_p), C.byref(n)))
         return self._out[:min(n.value, self.MAX_OUT)].copy()
+
+    def stats(self):
+        """{frames, total_ms, wait_ms, launches} of update_batch since creation (wait_ms = launch -> result of the association kernel)."""
+        o = (C.c_double * 4)()
+        check(lib().adas_tracker_stats(self._h, o))
+        return {"frames": int(o[0]), "total_ms": float(o[1]), "wait_ms": float(o[2]), "launches": int(o[3])}
 
     def update_batch(self, counts, boxes_xyxy, scores, class_ids, max_out: int = 256):
         """All frames of a step in one library call -> list (per frame) of TRACK_DTYPE record arrays."""

@@ -9,12 +9,14 @@
 #include "common.h"
 #include "../../include/adas_b200.h"
 #include <math.h>
+#include <time.h>
 #include <string.h>
 #include <algorithm>
 #include <memory>
 #include <utility>
 
 namespace adas {
+static inline uint64_t now_ns() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
 int launch_iou_cost(int problems, const double* a, const int32_t* a_off, const double* b, const int32_t* b_off,
                     const double* det_scores, int fuse, double* cost, const int64_t* cost_off, cudaStream_t st);
 int launch_lap(int problems, const double* cost, const int64_t* cost_off, const int32_t* T, const int32_t* D,
@@ -139,6 +141,8 @@ struct adas_tracker {
     double* h3_in_dev = nullptr; int32_t* h3_out_dev = nullptr;   // their device-side addresses
     int32_t* h_done = nullptr; int32_t* h_done_dev = nullptr; int32_t seq = 0;   // completion word the host spins on
     double* d_u = nullptr;                                    // row potentials of problems beyond the kernel's shared-memory budget
+    // wall-clock accounting of the update path (adas_tracker_stats): frames, total ns, ns between launch and result, launches
+    uint64_t st_frames = 0, st_total_ns = 0, st_wait_ns = 0, st_launches = 0;
     double* d3_in = nullptr; int32_t* d3_out = nullptr; double* d3_cost = nullptr; int32_t* d3_lists = nullptr;
     size_t cap3_in = 0, cap3_out = 0, cap3_cost = 0, cap3_lists = 0;
 };
@@ -269,6 +273,7 @@ static int assoc3_run(adas_tracker* t, const std::vector<TrackP>& pool, const st
     // publishes this frame's sequence number last; the host spins on it (and asks the stream now and then, so that a failed launch
     // or a device fault ends the wait with an error instead of a hang)
     const int32_t seq = ++t->seq;
+    const uint64_t w0 = now_ns();
     if (launch_assoc3(t->h3_in_dev, (int)n_in, t->d3_in, t->h3_out_dev, (int)n_out, t->d3_out, t->h_done_dev, seq, t->d3_cost, t->d_v, t->d_mv, t->d_wi,
                       t->d3_lists, t->d_u, t->st)) return 1;
     {
@@ -286,6 +291,7 @@ static int assoc3_run(adas_tracker* t, const std::vector<TrackP>& pool, const st
         }
         std::atomic_thread_fence(std::memory_order_acquire);
     }
+    t->st_wait_ns += now_ns() - w0; t->st_launches += 1;
     const int32_t* o = t->h3_out;
     for (int i = 0; i < P; ++i) (*m1)[i] = o[i];
     for (int i = 0; i < P; ++i) (*m2)[i] = o[P + i];
@@ -419,12 +425,20 @@ int adas_tracker_update_batch(adas_tracker* t, int n_frames, const int32_t* coun
     ADAS_CHECK(t != nullptr && n_frames >= 0 && counts != nullptr && n_out != nullptr, "adas_tracker_update_batch: bad arguments");
     ADAS_CUDA(cudaSetDevice(t->device));
     size_t off = 0;
+    const uint64_t t0 = adas::now_ns();
     for (int f = 0; f < n_frames; ++f) {
         int k = 0;
         if (update_one(t, counts[f], boxes_xyxy + off * 4, scores + off, class_ids + off, max_out, out ? out + (size_t)f * max_out : nullptr, &k)) return 1;
         n_out[f] = k;
         off += (size_t)counts[f];
     }
+    t->st_total_ns += adas::now_ns() - t0; t->st_frames += (uint64_t)n_frames;
+    return 0;
+}
+
+int adas_tracker_stats(adas_tracker* t, double* out4) {
+    ADAS_CHECK(t != nullptr && out4 != nullptr, "adas_tracker_stats: null argument");
+    out4[0] = (double)t->st_frames; out4[1] = (double)t->st_total_ns * 1e-6; out4[2] = (double)t->st_wait_ns * 1e-6; out4[3] = (double)t->st_launches;
     return 0;
 }
 

@@ -8,9 +8,13 @@
 // a 58 us im2col pass), and the layer is bound by writing its 64-channel output anyway.
 //
 // One warp owns 16 consecutive output pixels of one output row (the M of m16n8k16) and all Cout channels (NT n-tiles of 8):
-//   A fragments: 4-byte global loads (coalesced: 8 pixels x 16 B per request), predicated at the image border (the padded layout only
-//                has a one-pixel halo; k = 6 / 7 stems reach further out);
-//   B fragments: folded weights in shared memory, row stride K + 8 halves (conflict-free for the fragment pattern);
+//   k-slot permutation: a thread of the warp MMA holds k-slots {2t, 2t+1, 2t+8, 2t+9} of a 16-wide step.  Mapping those four slots to
+//                the four CONTIGUOUS halves 4t .. 4t+3 of the 32-byte row chunk (one pixel) for BOTH operands leaves the dot product
+//                unchanged and turns the fragment loads into one 8-byte load per operand row (instead of two 4-byte loads);
+//   A fragments: 8-byte global loads = one pixel (coalesced: 4 lanes x 8 B per output pixel), predicated at the image border (the padded
+//                layout only has a one-pixel halo; k = 6 / 7 stems reach further out);
+//   B fragments: folded weights in shared memory in plain [dy][dx*4 + c] order, row stride = 16 (mod 64) halves so that the 8-byte
+//                fragment loads of a half-warp hit distinct banks;
 //   epilogue:    + bias -> activation -> fp16 -> per-warp staging in shared memory -> 16-byte coalesced stores of interior pixels.
 // Accumulation is fp32 in a fixed order, independent of the batch size and of the grid: frame k of a batch equals the batch-1 result.
 //
@@ -39,13 +43,14 @@ struct StemParams {
     int B, Hp, Wp;          // padded input geometry (H + 2, W + 2)
     int Ho, Wo, out_ld;
     int k, pad, KR, K;      // K = k * KR
+    int w_ld;               // shared-memory row stride of the weights (halves)
     int act, tiles_per_row, total_tiles;
 };
 
 template <int NT>
 __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int w_ld = p.K + 8;                                         // halves
+    const int w_ld = p.w_ld;                                          // halves
     __half* ws = reinterpret_cast<__half*>(smem);
     __half* stg_all = ws + (size_t)NT * 8 * w_ld;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemPa
     __syncthreads();
     __half* stg = stg_all + warp * 16 * STEM_STG_LD;
     const int ksteps_row = p.KR >> 4;
-    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(p.img);   // one uint32 = 2 channels of a pixel
+    const uint2* img64 = reinterpret_cast<const uint2*>(p.img);         // one uint2 = one pixel (4 halves)
     for (int tile = blockIdx.x * STEM_WARPS + warp; tile < p.total_tiles; tile += gridDim.x * STEM_WARPS) {
         const int b = tile / (p.Ho * p.tiles_per_row);
         const int r = tile - b * (p.Ho * p.tiles_per_row);
@@ -76,23 +81,18 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_s2_kernel(const StemPa
             const bool row_ok = row >= 0 && row < p.Hp;
             const size_t row_base = ((size_t)b * p.Hp + (row_ok ? row : 0)) * p.Wp;
             for (int ks = 0; ks < ksteps_row; ++ks) {
-                // k index inside the row: ks*16 + {2t, 2t+1} and + 8 -> pixel dx = kidx / 4, channel pair (kidx % 4) / 2
-                const int k_lo = ks * 16 + 2 * t, k_hi = k_lo + 8;
-                const int dx_lo = k_lo >> 2, dx_hi = k_hi >> 2, cp_lo = (k_lo & 3) >> 1, cp_hi = (k_hi & 3) >> 1;
-                uint32_t a[4];
-                auto ld = [&](int col, int cp) -> uint32_t {
-                    return (row_ok && col >= 0 && col < p.Wp) ? __ldg(img32 + (row_base + col) * 2 + cp) : 0u;
+                // lane t of a pixel group holds pixel dx = ks*4 + t of this filter row: halves (dx*4 .. dx*4+3) = k-slots {2t, 2t+1, 2t+8, 2t+9}
+                const int dx = ks * 4 + t;
+                auto ld = [&](int col) -> uint2 {
+                    return (row_ok && col >= 0 && col < p.Wp) ? __ldg(img64 + row_base + col) : make_uint2(0u, 0u);
                 };
-                a[0] = ld(col_g + dx_lo, cp_lo);
-                a[1] = ld(col_g8 + dx_lo, cp_lo);
-                a[2] = ld(col_g + dx_hi, cp_hi);
-                a[3] = ld(col_g8 + dx_hi, cp_hi);
-                const __half* wrow = ws + (size_t)g * w_ld + dy * p.KR + ks * 16 + 2 * t;
+                const uint2 lo = ld(col_g + dx), hi = ld(col_g8 + dx);
+                const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+                const __half* wrow = ws + (size_t)g * w_ld + dy * p.KR + ks * 16 + 4 * t;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + (size_t)j * 8 * w_ld);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + (size_t)j * 8 * w_ld + 8);
-                    mma_m16n8k16(acc[j], a, b0, b1);
+                    const uint2 bw = *reinterpret_cast<const uint2*>(wrow + (size_t)j * 8 * w_ld);
+                    mma_m16n8k16(acc[j], a, bw.x, bw.y);
                 }
             }
         }
@@ -135,7 +135,11 @@ int launch_stem_conv_s2(const __half* img, int B, int H, int W, const __half* wq
     p.k = k; p.pad = pad; p.KR = (4 * k + 15) / 16 * 16; p.K = k * p.KR; p.act = act;
     p.tiles_per_row = (Wo + 15) / 16;
     p.total_tiles = B * Ho * p.tiles_per_row;
-    const int smem = Cout * (p.K + 8) * 2 + STEM_WARPS * 16 * STEM_STG_LD * 2;
+    // weight row stride = 16 (mod 64) halves: the 8-byte fragment loads of a half-warp (4 rows x 4 lanes) then cover all 32 banks once;
+    // K + 8 (2-way conflicts) only where the conflict-free stride would not fit 48 KB
+    p.w_ld = p.K + ((16 - p.K % 64) + 64) % 64;
+    if (Cout * p.w_ld * 2 + STEM_WARPS * 16 * STEM_STG_LD * 2 > 48 * 1024) p.w_ld = p.K + 8;
+    const int smem = Cout * p.w_ld * 2 + STEM_WARPS * 16 * STEM_STG_LD * 2;
     ADAS_CHECK(smem <= 48 * 1024, "stem_conv: %d bytes of shared memory", smem);
     int blocks = (p.total_tiles + STEM_WARPS - 1) / STEM_WARPS;
     int n_sms = 148;

@@ -546,3 +546,32 @@ def test_two_devices_in_one_process():
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
     assert np.array_equal(res[0][3], res[1][3])
+
+
+def test_engine_from_onnx_file_matches_state_dict_plan(tmp_path):
+    """SURVEY 8f rank 2 on the device: `B200Engine("model.onnx")` (a file written by torch's exporter from the oracle network, BatchNorm
+    fused the way ultralytics exports it) against the engine built from the state_dict plan and against the fp32 oracle.  The two
+    plans' packed weights differ by at most one fp16 ulp (BN folded in fp32 by the exporter, in fp64 by plan.Weights), so the outputs
+    agree to the fp16 noise floor rather than bit for bit; both stay within the 1e-3 contract of the oracle."""
+    import test_onnx_import as toi
+    W = plan.synth_weights("yolov5", 0)
+    model = nets.build("yolov5", W.state_dict, scale="n")
+    onnx_path = str(tmp_path / "yolov5n.onnx")
+    toi._export(toi._fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), onnx_path)
+    os.environ["ADAS_B200_PLAN_CACHE"] = str(tmp_path / "cache")
+    try:
+        e_onnx = B200Engine(onnx_path, device=0, max_batch=2)
+    finally:
+        os.environ.pop("ADAS_B200_PLAN_CACHE", None)
+    path, _, _ = cached_plan("yolov5", scale="n")
+    e_sd = B200Engine(path, device=0, max_batch=2)
+    assert e_onnx.get_engine_input_shape() == e_sd.get_engine_input_shape() == [1, 3, 640, 640]
+    assert e_onnx.get_engine_output_shape() == e_sd.get_engine_output_shape()
+    x = _blob([synth.frame(s) for s in (0, 1)])
+    a, b = e_onnx.engine_inference(x)[0], e_sd.engine_inference(x)[0]
+    with torch.no_grad():
+        ref = model(torch.from_numpy(x)).numpy()
+    d_ab = _report("v5n onnx-plan vs state_dict-plan prob", a[..., 4:], b[..., 4:])
+    d_ref = _report("v5n onnx-plan vs fp32 oracle prob", a[..., 4:], ref[..., 4:])
+    assert d_ab < 1e-3 and d_ref < 1e-3
+    assert _report("v5n onnx-plan box px", a[..., :4], ref[..., :4]) < 0.5

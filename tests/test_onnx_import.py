@@ -147,6 +147,22 @@ def test_ufldv2_reference_style_export(tmp_path):
     os.remove(path)                                  # 0.8 GB (the 2048 -> 91224 classifier): do not leave it in the pytest tmp dir
 
 
+def test_ufldv2_tusimple_export_is_recognised(tmp_path):
+    """A TuSimple export (320x800 input, no LayerNorm before the classifier, 100x56 / 100x41 heads): the plan carries dataset id 1."""
+    W = plan.synth_weights("ufldv2", 6)
+    ref = plan.build_ufldv2(W, "18", "tusimple")
+    cfg = {k: v for k, v in plan.UFLD_TUSIMPLE.items() if k not in ("dataset", "crop_ratio")}
+    path = str(tmp_path / "tusimple_18.onnx")
+    _export(nets.build("ufldv2", W.state_dict, backbone="18", **cfg), (1, 3, 320, 800), path)
+    m = onnx_import.read_onnx(path)
+    spec = onnx_import.recognise(m)
+    assert (spec.kind, spec.scale, spec.in_h, spec.in_w) == ("ufldv2", "18", 320, 800)
+    got = onnx_import.build_plan(m, spec)
+    assert got.meta[:7] == ref.meta[:7] and got.meta[6] == 1
+    _assert_same_plan(ref, got, "ufldv2-18 tusimple")
+    os.remove(path)
+
+
 def test_wrong_architecture_is_reported(tmp_path):
     W = plan.synth_weights("yolov5", 6)
     plan.build_yolov5(W, "n")                     # materialises the seeded state_dict

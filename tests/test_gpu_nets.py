@@ -555,6 +555,7 @@ def test_engine_from_onnx_file_matches_state_dict_plan(tmp_path):
     agree to the fp16 noise floor rather than bit for bit; both stay within the 1e-3 contract of the oracle."""
     import test_onnx_import as toi
     W = plan.synth_weights("yolov5", 0)
+    plan.build_yolov5(W, "n")                      # the seeded state_dict is generated as the builder asks for each tensor
     model = nets.build("yolov5", W.state_dict, scale="n")
     onnx_path = str(tmp_path / "yolov5n.onnx")
     toi._export(toi._fuse_conv_bn(nets.build("yolov5", W.state_dict, scale="n")), (1, 3, 640, 640), onnx_path)

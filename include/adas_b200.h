@@ -135,6 +135,32 @@ int adas_ufld_postprocess(int device, const float* heads_host, int batch, int nu
                           const double* col_anchor, int32_t* pts, int32_t* npts,
                           uint8_t* status, double* coords_f);
 
+/* ---- lane geometry downstream of the lane decode --------------------------------------------------------
+ * Replaces, per frame: LaneDetectBase.__update_lanes_status / __update_lanes_area / __adjust_lanes_points
+ * (TrafficLaneDetector/ufldDetector/core.py:102-158: ego-lane polygon, optional degree-2 np.polyfit resampling on
+ * np.linspace(miny, maxy, image_height)), PerspectiveTransformation.transformToBirdViewPoints
+ * (perspectiveTransformation.py:120-142) and the arithmetic of calcCurveAndOffset (perspectiveTransformation.py:145-208; the
+ * arrows and text it draws on the bird-view image stay with the host drawing code). */
+typedef struct adas_lane_geom {
+    int32_t area_status;   /* LaneInfo.area_status: both ego lanes detected */
+    int32_t n_area;        /* points of the ego-lane polygon: left ++ flipud(right) */
+    int32_t n_bird[4];     /* bird-view points per lane (0 when no matrix was given) */
+    int32_t direction;     /* curvature_direction: -1 "L", 0 "F", 1 "R", 2 = None (an ego lane is missing) */
+    int32_t pad;
+    double curvature;      /* metres; valid when direction != 2 */
+    double offset;         /* distance_from_center, metres; valid when direction != 2 */
+} adas_lane_geom;
+
+/* From host arrays shaped like adas_ufld_detect's outputs: pts [batch,4,max_pts,2] int32, npts [batch,4], status [batch,4].
+ * M: [batch,9] row-major float64 frontal->bird-view matrices (PerspectiveTransformation.M after updateTransformParams) or NULL to
+ * skip the bird view.  area: [batch,cap_area,2] (cap_area >= 2*max_pts, and >= 2*img_h with adjust_lanes), bird: [batch,4,max_pts,2]. */
+int adas_lane_geometry(int device, const int32_t* pts, const int32_t* npts, const uint8_t* status, int batch, int max_pts, int img_w,
+                       int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h, int32_t* area, int cap_area, int32_t* bird,
+                       adas_lane_geom* out);
+/* Same, on the lane points the engine's last adas_ufld_detect / adas_detect_pair left on the device (no upload of the points). */
+int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h,
+                            int32_t* area, int cap_area, int32_t* bird, adas_lane_geom* out);
+
 /* UFLD pre-processing alone (row H): u8 BGR host -> fp32 NCHW host [batch,3,in_h,in_w] */
 int adas_ufld_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W,
                          int in_h, int in_w, double crop_ratio, float* blob_nchw_host);

@@ -576,3 +576,25 @@ def test_engine_from_onnx_file_matches_state_dict_plan(tmp_path):
     d_ref = _report("v5n onnx-plan vs fp32 oracle prob", a[..., 4:], ref[..., 4:])
     assert d_ab < 1e-3 and d_ref < 1e-3
     assert _report("v5n onnx-plan box px", a[..., :4], ref[..., :4]) < 0.5
+
+
+def test_lane_geometry_from_resident_points_equals_standalone_call():
+    """adas_ufld_lane_geometry works on the lane points the last lane detect left on the device: same results as uploading the
+    points adas_ufld_detect returned (polygon, bird-view points, curvature / offset), with and without the polyfit resampling."""
+    from adas_b200.TrafficLaneDetector.ufldDetector.perspectiveTransformation import PerspectiveTransformation
+    path, _, _ = cached_plan("ufldv2", backbone="18", cfg="culane")
+    eng = _capi.Engine(path, 0, max_batch=4)
+    frames = np.stack([synth.frame(s) for s in range(4)])
+    pts, npts, status, _ = eng.ufld_detect(frames)
+    M = PerspectiveTransformation((1280, 720)).M
+    for adjust in (False, True):
+        a = eng.lane_geometry(4, (1280, 720), adjust_lanes=adjust, M=M)
+        b = _capi.lane_geometry(pts, npts, status, (1280, 720), adjust_lanes=adjust, M=M)
+        for ra, rb in zip(a, b):
+            assert ra["area_status"] == rb["area_status"] and np.array_equal(ra["area"], rb["area"])
+            assert all(np.array_equal(x, y) for x, y in zip(ra["bird"], rb["bird"]))
+            assert ra["direction"] == rb["direction"] and ra["curvature"] == rb["curvature"] and ra["offset"] == rb["offset"]
+    print("[lane geometry] area_status", [r["area_status"] for r in a], "directions", [r["direction"] for r in a])
+    with pytest.raises(Exception):
+        _capi.Engine(path, 0, max_batch=1).lane_geometry(1, (1280, 720))       # no lane detect has run on that engine
+    eng.close()

@@ -144,3 +144,76 @@ def test_ufld_post_matches_reference_golden(golden_dir, hw):
             for j in bad:
                 assert np.abs(diff[j]).max() == 1 and abs(c[j] - round(c[j])) < 1e-3, (key, l, j, got[j], gold[j], c[j])
         assert np.array_equal(status[b], g[key + "_status"])
+
+
+# ---- lane geometry on the device (SURVEY rows K + 8f-1; csrc/lane_geom.cu) ------------------------------------------------------
+def _lanes_to_arrays(lanes_per_frame, status_per_frame, mp=81):
+    B = len(lanes_per_frame)
+    pts = np.zeros((B, 4, mp, 2), np.int32)
+    npts = np.zeros((B, 4), np.int32)
+    for b, lanes in enumerate(lanes_per_frame):
+        for l in range(4):
+            a = np.asarray(lanes[l], np.int32).reshape(-1, 2)
+            pts[b, l, :len(a)] = a
+            npts[b, l] = len(a)
+    return pts, npts, np.asarray(status_per_frame, np.uint8).reshape(B, 4)
+
+
+def _assert_points(got, want, what):
+    """integer points must match; a +-1 step is tolerated only where the device's float64 least-squares solution may sit on the other
+    side of an integer than LAPACK's (rare: the two solutions agree to ~1e-12 relative)"""
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    assert d.max(initial=0) <= 1, (what, int(d.max()))
+    assert (d > 0).sum() <= max(1, got.shape[0] // 200), (what, int((d > 0).sum()))
+
+
+@pytest.mark.parametrize("adjust", [False, True])
+def test_lane_area_on_device_matches_reference_golden(golden_dir, adjust):
+    """ego-lane polygon and the degree-2 polyfit resampling (core.py:102-158) for a batch of frames in one launch, against the
+    UNMODIFIED reference class's `_area` / `_area_adj` / `_area_status` (tests/golden/ufld_post.npz)."""
+    g = np.load(os.path.join(golden_dir, "ufld_post.npz"))
+    keys = ["s0_720x1280", "s1_720x1280", "s2_720x1280", "s3_720x1280"]
+    lanes = [[g[f"{k}_lane{l}"] for l in range(4)] for k in keys]
+    pts, npts, status = _lanes_to_arrays(lanes, [g[k + "_status"] for k in keys])
+    res = _capi.lane_geometry(pts, npts, status, (1280, 720), adjust_lanes=adjust)
+    for k, r in zip(keys, res):
+        assert r["area_status"] == bool(g[k + "_area_status"][0]), k
+        want = g[k + ("_area_adj" if adjust else "_area")].astype(np.int32).reshape(-1, 2)
+        _assert_points(r["area"], want, (k, adjust))
+        if not adjust:
+            assert np.array_equal(r["area"], want)
+    # another image height (480x640 golden case): its own launch
+    k = "s0_480x640"
+    pts, npts, status = _lanes_to_arrays([[g[f"{k}_lane{l}"] for l in range(4)]], [g[k + "_status"]])
+    r = _capi.lane_geometry(pts, npts, status, (640, 480), adjust_lanes=adjust)[0]
+    _assert_points(r["area"], g[k + ("_area_adj" if adjust else "_area")].astype(np.int32).reshape(-1, 2), (k, adjust))
+
+
+def test_birdview_points_and_curvature_on_device_match_reference_golden(golden_dir):
+    """transformToBirdViewPoints + calcCurveAndOffset (perspectiveTransformation.py:120-208) for 32 cases (8 lane pairs x the matrices
+    after each updateTransformParams type), against the reference class's own results (tests/golden/birdview.npz)."""
+    g = np.load(os.path.join(golden_dir, "birdview.npz"))
+    cases = [(s, k) for s in range(8) for k in ("Default", "Top", "Bottom", None)]
+    lanes, Ms = [], []
+    for case, (seed, kind) in enumerate(cases):
+        left, right = synth.ego_lanes(100 + seed)
+        lanes.append([[], left, right, []])
+        Ms.append(g[f"c{case}_M"])
+    pts, npts, status = _lanes_to_arrays(lanes, [[0, 1, 1, 0]] * len(cases))
+    res = _capi.lane_geometry(pts, npts, status, (1280, 720), adjust_lanes=False, M=np.stack(Ms), bird_wh=(1280, 720))
+    worst_c = worst_o = 0.0
+    for case, r in enumerate(res):
+        _assert_points(r["bird"][1], g[f"c{case}_bl"].astype(np.int32).reshape(-1, 2), (case, "left"))
+        _assert_points(r["bird"][2], g[f"c{case}_br"].astype(np.int32).reshape(-1, 2), (case, "right"))
+        d, curv, off = g[f"c{case}_curve"]
+        if np.array_equal(r["bird"][1], g[f"c{case}_bl"]) and np.array_equal(r["bird"][2], g[f"c{case}_br"]):
+            assert {"L": -1.0, "F": 0.0, "R": 1.0}[r["direction"]] == d, case
+            worst_c = max(worst_c, abs(r["curvature"] - curv) / abs(curv))
+            worst_o = max(worst_o, abs(r["offset"] - off) / max(1e-6, abs(off)))
+    print(f"[parity] bird-view curvature rel err {worst_c:.2e}, offset rel err {worst_o:.2e} over {len(cases)} cases")
+    assert worst_c < 1e-8 and worst_o < 1e-8
+    # a missing ego lane -> (None, None), None
+    pts, npts, status = _lanes_to_arrays([[[], synth.ego_lanes(100)[0], [], []]], [[0, 1, 0, 0]])
+    r = _capi.lane_geometry(pts, npts, status, (1280, 720), M=Ms[0])[0]
+    assert r["direction"] is None and r["curvature"] is None and r["offset"] is None and not r["area_status"] and len(r["area"]) == 0

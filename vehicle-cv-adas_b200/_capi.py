@@ -21,7 +21,7 @@ SYMBOLS = [
     "adas_last_error", "adas_version", "adas_launch_count", "adas_engine_create", "adas_engine_destroy",
     "adas_engine_model_kind", "adas_engine_meta", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
-    "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
+    "adas_ufld_detect", "adas_ufld_postprocess", "adas_lane_geometry", "adas_ufld_lane_geometry", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
     "adas_comm_unique_id", "adas_comm_create", "adas_comm_destroy", "adas_comm_all_gather", "adas_comm_sync", "adas_comm_read", "adas_comm_info",
@@ -248,6 +248,18 @@ class Engine:
                                      _p(counts, C.c_int32), _p(ncand, C.c_int32)))
         return boxes, scores, cls, idx, counts, ncand
 
+    def lane_geometry(self, batch: int, img_wh, adjust_lanes: bool = False, M=None, bird_wh=(1280, 720)):
+        """lane polygon / polyfit resampling / bird-view points / curvature + offset of the frames of the LAST ufld_detect (or
+        detect_pair) on this engine, computed from the lane points still resident on the device."""
+        mp = max(self.output_shapes[0][2], self.output_shapes[1][2])
+        cap, area, bird, out = _lane_geom_outputs(batch, mp, img_wh[1], adjust_lanes)
+        Mb = None
+        if M is not None:
+            Mb = as_c(np.broadcast_to(np.asarray(M, np.float64).reshape(-1, 3, 3), (batch, 3, 3)), np.float64)
+        check(lib().adas_ufld_lane_geometry(self._h, batch, img_wh[0], img_wh[1], 1 if adjust_lanes else 0, _p(Mb, C.c_double) if Mb is not None else None,
+                                            bird_wh[0], bird_wh[1], _p(area, C.c_int32), cap, _p(bird, C.c_int32), out.ctypes.data_as(C.c_void_p)))
+        return _lane_geom_result(area, bird, out, Mb is not None)
+
     def ufld_detect(self, frames, on_device: bool = False, shape=None, want_coords: bool = False):
         if on_device:
             ptr, (B, H, W) = frames, shape
@@ -338,6 +350,44 @@ def ufld_postprocess(heads: np.ndarray, dims, img_wh, row_anchor, col_anchor, de
                                       _p(ca, C.c_double), _p(pts, C.c_int32), _p(npts, C.c_int32), _p(status, C.c_uint8),
                                       _p(coords, C.c_double)))
     return pts, npts, status, coords
+
+
+LANE_GEOM_DTYPE = np.dtype([("area_status", "<i4"), ("n_area", "<i4"), ("n_bird", "<i4", (4,)), ("direction", "<i4"), ("pad", "<i4"),
+                            ("curvature", "<f8"), ("offset", "<f8")])
+assert LANE_GEOM_DTYPE.itemsize == 48          # struct adas_lane_geom (include/adas_b200.h)
+
+
+def _lane_geom_outputs(B, mp, img_h, adjust):
+    cap = max(2 * mp, 2 * img_h if adjust else 0)
+    return cap, np.zeros((B, cap, 2), np.int32), np.zeros((B, 4, mp, 2), np.int32), np.zeros(B, LANE_GEOM_DTYPE)
+
+
+def _lane_geom_result(area, bird, out, have_M):
+    """list per frame of dict(area_status, area [n,2], bird [4 arrays] or None, direction 'L'/'F'/'R'/None, curvature, offset)"""
+    res = []
+    for b in range(out.shape[0]):
+        o = out[b]
+        d = {-1: "L", 0: "F", 1: "R"}.get(int(o["direction"]))
+        res.append({"area_status": bool(o["area_status"]), "area": area[b, :int(o["n_area"])].copy(),
+                    "bird": [bird[b, l, :int(o["n_bird"][l])].copy() for l in range(4)] if have_M else None,
+                    "direction": d, "curvature": float(o["curvature"]) if d is not None else None,
+                    "offset": float(o["offset"]) if d is not None else None})
+    return res
+
+
+def lane_geometry(pts, npts, status, img_wh, adjust_lanes: bool = False, M=None, bird_wh=(1280, 720), device: int = 0):
+    """Rows K + 8f-1 on the device from host arrays shaped like ufld_detect's outputs (see adas_lane_geometry in include/adas_b200.h).
+    M: one 3x3 matrix for all frames or [B,3,3]."""
+    pts, npts, status = as_c(pts, np.int32), as_c(npts, np.int32), as_c(status, np.uint8)
+    B, _, mp, _ = pts.shape
+    cap, area, bird, out = _lane_geom_outputs(B, mp, img_wh[1], adjust_lanes)
+    Mb = None
+    if M is not None:
+        Mb = as_c(np.broadcast_to(np.asarray(M, np.float64).reshape(-1, 3, 3), (B, 3, 3)), np.float64)
+    check(lib().adas_lane_geometry(device, _p(pts, C.c_int32), _p(npts, C.c_int32), _p(status, C.c_uint8), B, mp, img_wh[0], img_wh[1],
+                                   1 if adjust_lanes else 0, _p(Mb, C.c_double) if Mb is not None else None, bird_wh[0], bird_wh[1],
+                                   _p(area, C.c_int32), cap, _p(bird, C.c_int32), out.ctypes.data_as(C.c_void_p)))
+    return _lane_geom_result(area, bird, out, Mb is not None)
 
 
 def iou_cost(a_list, b_list, scores_list=None, device: int = 0):

@@ -9,6 +9,8 @@
 #include <vector>
 #include <atomic>
 
+struct adas_lane_geom;      // include/adas_b200.h
+
 namespace adas {
 
 // ---- error plumbing -----------------------------------------------------------------------
@@ -106,6 +108,9 @@ int launch_fc_stream(const __half* x, int x_ld, int batch, const __half* W, int 
                      int out_f32, cudaStream_t st);
 int launch_nchw_to_padded(const float* in, int B, int C, int H, int W, __half* out, int out_ld, cudaStream_t st);
 int launch_stempack(const __half* img, int B, int H, int W, __half* q, cudaStream_t st);
+// lane_geom.cu: ego-lane polygon / polyfit resampling / bird-view points / curvature + offset, one block per frame
+int launch_lane_geom(const int32_t* pts, const int32_t* npts, const uint8_t* status, const double* M, int batch, int max_pts, int img_w, int img_h,
+                     int adjust, int bird_w, int bird_h, int32_t* area, int cap_area, int32_t* bird, ::adas_lane_geom* out, cudaStream_t st);
 // stem_conv.cu: k x k stride-2 conv of the padded C=4 image (warp-level MMA, no patch matrix)
 int stem_conv_supported(int Cout, int k, int pad);
 int launch_stem_conv_s2(const __half* img, int B, int H, int W, const __half* wq, const float* bias, int Cout, int k, int pad, int act,

@@ -83,6 +83,8 @@ struct adas_engine {
     double* d_row_anchor = nullptr;
     double* d_col_anchor = nullptr;
     int32_t* d_pts = nullptr; int32_t* d_npts = nullptr; uint8_t* d_status = nullptr; double* d_coords = nullptr;
+    // lane geometry downstream of the lane decode (lane_geom.cu), allocated on first use
+    int32_t* d_area = nullptr; int32_t* d_bird = nullptr; adas_lane_geom* d_geom = nullptr; double* d_M = nullptr; int geom_cap_area = 0; int ufld_last_batch = 0;
     int ufld_max_pts = 0;
     double ufld_crop = 0.6;       // crop ratio of the plan's dataset (ModelConfig.crop_ratio)
     std::vector<int32_t> h_ncand;
@@ -812,6 +814,7 @@ int adas_engine_destroy(adas_engine* e) {
     for (auto& kv : e->programs) if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
     for (auto& b : e->dbufs) cudaFree(b.ptr);
     cudaFree(e->d_blob); cudaFree(e->d_input); cudaFree(e->d_frames); cudaFree(e->d_raw); cudaFree(e->d_lut);
+    cudaFree(e->d_area); cudaFree(e->d_bird); cudaFree(e->d_geom); cudaFree(e->d_M);
     cudaFree(e->d_row_anchor); cudaFree(e->d_col_anchor); cudaFree(e->d_pts); cudaFree(e->d_npts); cudaFree(e->d_status); cudaFree(e->d_coords);
     if (e->ev_frames) cudaEventDestroy(e->ev_frames);
     if (e->yp.flags) free_yolo_post(&e->yp);
@@ -1001,8 +1004,36 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     ADAS_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
     if (coords_f) ADAS_CUDA(cudaMemcpyAsync(coords_f, e->d_coords, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost, e->stream));
     ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    e->ufld_last_batch = batch;
     tr.mark("post+d2h");
     tr.report();
+    return 0;
+}
+
+int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h, int32_t* area,
+                            int cap_area, int32_t* bird, adas_lane_geom* out) {
+    ADAS_CHECK(e != nullptr && e->hdr.model_kind == ADAS_MODEL_UFLDV2, "adas_ufld_lane_geometry needs a UFLDv2 engine");
+    ADAS_CHECK(batch >= 1 && batch <= e->ufld_last_batch, "adas_ufld_lane_geometry: batch %d, but the last lane detect on this engine decoded %d frames", batch, e->ufld_last_batch);
+    ADAS_CHECK(area != nullptr && out != nullptr && (M == nullptr || bird != nullptr), "adas_ufld_lane_geometry: null argument");
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const int mp = e->ufld_max_pts;
+    if (e->d_geom == nullptr || e->geom_cap_area < cap_area) {
+        cudaFree(e->d_area); cudaFree(e->d_bird); cudaFree(e->d_geom); cudaFree(e->d_M);
+        e->d_area = nullptr; e->d_bird = nullptr; e->d_geom = nullptr; e->d_M = nullptr;
+        ADAS_CUDA(cudaMalloc(&e->d_area, (size_t)e->max_batch * cap_area * 8));
+        ADAS_CUDA(cudaMalloc(&e->d_bird, (size_t)e->max_batch * 4 * mp * 8));
+        ADAS_CUDA(cudaMalloc(&e->d_geom, (size_t)e->max_batch * sizeof(adas_lane_geom)));
+        ADAS_CUDA(cudaMalloc(&e->d_M, (size_t)e->max_batch * 72));
+        e->geom_cap_area = cap_area;
+    }
+    // the decoded points of the last adas_ufld_detect / adas_detect_pair are still resident (d_pts, d_npts, d_status): no re-upload
+    if (M) ADAS_CUDA(cudaMemcpyAsync(e->d_M, M, (size_t)batch * 72, cudaMemcpyHostToDevice, e->stream));
+    if (launch_lane_geom(e->d_pts, e->d_npts, e->d_status, M ? e->d_M : nullptr, batch, mp, img_w, img_h, adjust_lanes, bird_w, bird_h, e->d_area, cap_area,
+                         e->d_bird, e->d_geom, e->stream)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(area, e->d_area, (size_t)batch * cap_area * 8, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaMemcpyAsync(out, e->d_geom, (size_t)batch * sizeof(adas_lane_geom), cudaMemcpyDeviceToHost, e->stream));
+    if (M) ADAS_CUDA(cudaMemcpyAsync(bird, e->d_bird, (size_t)batch * 4 * mp * 8, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -1063,6 +1094,7 @@ int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames
         ADAS_CUDA(cudaMemcpyAsync(pts, u->d_pts, (size_t)batch * 4 * mp * 2 * 4, cudaMemcpyDeviceToHost, u->stream));
         ADAS_CUDA(cudaMemcpyAsync(npts, u->d_npts, (size_t)batch * 4 * 4, cudaMemcpyDeviceToHost, u->stream));
         ADAS_CUDA(cudaMemcpyAsync(status, u->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, u->stream));
+        u->ufld_last_batch = batch;
     }
     if (copy_yolo_results_finish(e->yp, batch, max_det, counts, n_candidates, e->h_ncand.data(), e->stream)) return 1;
     ADAS_CUDA(cudaStreamSynchronize(ufld->stream));

@@ -60,7 +60,9 @@ def build_plans(seed: int = 0):
     CACHE = plan.cache_dir()
     out = {}
     for kind, builder, kw in (("yolov8", plan.build_yolov8, dict(scale="l")), ("ufldv2", plan.build_ufldv2, dict(backbone="34"))):
-        path = os.path.join(CACHE, f"bench_{kind}_s{seed}_workload.b200w")
+        import zlib
+        prof = zlib.crc32(repr((plan.SYNTH_PROFILES.get(kind), plan.SYNTH_PROFILES_WORKLOAD.get(kind), plan.PLAN_VERSION)).encode()) & 0xffff
+        path = os.path.join(CACHE, f"bench_{kind}_s{seed}_workload_{prof:04x}.b200w")
         W = plan.synth_weights(kind, seed, variant=kw.get("scale", kw.get("backbone")), workload=True)
         pb = builder(W, **kw)
         if not os.path.isfile(path):

@@ -30,7 +30,9 @@ def halo_is_zero(buf: np.ndarray, B: int, H: int, W: int) -> bool:
 def cached_plan(kind: str, seed: int = 0, **kw):
     """Build (once per process tree) the synthetic plan + return (path, Weights-like state_dict)."""
     CACHE = plan.cache_dir()
-    tag = kind + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items())) + f"_s{seed}"
+    import zlib
+    prof = zlib.crc32(repr((plan.SYNTH_PROFILES.get(kind), plan.PLAN_VERSION)).encode()) & 0xffff      # a changed operating point is a new plan
+    tag = kind + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items())) + f"_s{seed}_{prof:04x}"
     path = os.path.join(CACHE, tag + ".b200w")
     variant = kw.get("scale", kw.get("backbone"))             # calibrated BatchNorm statistics exist for the tested variants
     W = plan.synth_weights(kind, seed, variant=variant)

@@ -153,7 +153,9 @@ SYNTH_PROFILES = {
                "fill": [(r"model\.22\.cv3\.\d\.2\.bias", -3.5)]},
     "yolov5": {"gains": [(r"model\.24\.m\.\d\.weight", 20.0)],
                "fill": [(r"model\.24\.m\.\d\.bias", -2.7)]},
-    "ufldv2": {},
+    # lane existence: random heads give P(valid) = 0.5 per anchor, i.e. no lane passes the "more than half / a quarter of the anchors
+    # valid" test and nothing downstream of the decode is exercised; +1.0 on the "valid" logits makes ~88 % of the anchors valid
+    "ufldv2": {"ufld_exist_bias": 1.0},
 }
 
 
@@ -613,6 +615,15 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
     b1 = W.get("cls.1.bias", (mid,), "bias")
     w2 = W.get("cls.3.weight", (total_dim, mid), "linear")
     b2 = W.get("cls.3.bias", (total_dim,), "bias")
+    exist_bias = None if W.real else W.profile.get("ufld_exist_bias")
+    if exist_bias and not getattr(W, "_ufld_exist_applied", False):
+        # synthetic operating point (see SYNTH_PROFILES): shift the "valid" planes of exist_row / exist_col, in the shared state_dict
+        b2 = b2.copy()
+        d12 = ngr * ncr * nl + ngc * ncc * nl
+        b2[d12 + ncr * nl:d12 + 2 * ncr * nl] += np.float32(exist_bias)
+        b2[total_dim - ncc * nl:] += np.float32(exist_bias)
+        W.state_dict["cls.3.bias"] = b2
+        W._ufld_exist_applied = True
     pb.flops_per_img += 2 * (mid * input_dim + total_dim * mid)
     w1p = np.zeros((mid, slab), np.float32)
     w1p[:, j_idx] = w1[:, f_idx]

@@ -449,15 +449,29 @@ def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
         with torch.no_grad():
             heads = [o.numpy() for o in cpu.ufld(torch.from_numpy(x))]
         opts, ost, _ = post.ufld_decode(heads, 1280, 720, post.CULANE_ROW_ANCHOR, post.CULANE_COL_ANCHOR)
-        tie = min(float(np.abs(heads[2][0, 1] - heads[2][0, 0]).min()), float(np.abs(heads[3][0, 1] - heads[3][0, 0]).min())) < 2e-2
-        if not tie:
-            assert [bool(v) for v in r.lane_status[b]] == ost, f
-            for l in range(4):
-                m = int(r.lane_npts[b, l])
-                if m == len(opts[l]):
-                    if m:
-                        assert np.abs(r.lane_pts[b, l, :m] - np.array(opts[l], np.int32).reshape(-1, 2)).max() <= 1, (f, l)
-                    n_lane_pts += m
+        for l in range(4):
+            is_row = l in (1, 2)
+            loc, ex = heads[0 if is_row else 1][0, :, :, l], heads[2 if is_row else 3][0, :, :, l]      # [grid, cls], [2, cls]
+            ncls = loc.shape[1]
+            valid_o = ex.argmax(0)
+            thr = ncls / 2 if is_row else ncls / 4
+            if abs(int(valid_o.sum()) - thr) < 3:
+                continue                                        # the lane-level decision itself sits on the threshold
+            assert bool(r.lane_status[b][l]) == ost[l], (f, l)
+            # points are matched by their anchor coordinate (y of a row anchor / x of a column anchor: unique per anchor)
+            key = 1 if is_row else 0
+            got = {int(p[key]): int(p[1 - key]) for p in r.lane_pts[b, l, :int(r.lane_npts[b, l])]}
+            want = {int(p[key]): int(p[1 - key]) for p in opts[l]}
+            anchors = (post.CULANE_ROW_ANCHOR * 720 if is_row else post.CULANE_COL_ANCHOR * 1280).astype(int)
+            for k in range(ncls):
+                top = np.sort(loc[:, k])[-2:]
+                if abs(float(ex[1, k] - ex[0, k])) <= 2e-2 or float(top[1] - top[0]) <= 2e-2:
+                    continue                                    # existence or argmax of this anchor is a near-tie in the oracle itself
+                a = int(anchors[k])
+                assert (a in got) == (a in want) == bool(valid_o[k]), (f, l, k)
+                if valid_o[k]:
+                    assert abs(got[a] - want[a]) <= 1, (f, l, k, got[a], want[a])
+                    n_lane_pts += 1
         # tracker: both sides see the same detections while every frame so far was exact
         prefix_ok = prefix_ok and ok
         bxr = det["boxes"]
@@ -471,7 +485,7 @@ def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
     pipe.close()
     print(f"[parity] frames -> detections / lanes / tracks vs the CPU reference path: {exact}/16 frames exact ({margin_frames} margin frames), "
           f"{n_det} detections, {n_tracks_cmp} track records and {n_lane_pts} lane points compared")
-    assert exact >= 6 and n_det > 0 and n_tracks_cmp > 0
+    assert exact >= 6 and n_det > 0 and n_tracks_cmp > 0 and n_lane_pts > 1000
 
 
 @pytest.mark.parametrize("kind,kw,B", [("yolov8", dict(scale="l"), 4), ("ufldv2", dict(backbone="34"), 4), ("yolov5", dict(scale="n"), 2)])

@@ -1,21 +1,29 @@
-// gemm_v3.cu -- the product GEMM / implicit-GEMM conv kernel (round 2): persistent, warp-specialised tcgen05 kernel with a
-// shared-memory staged, TMA-stored epilogue.
+// gemm_v3.cu -- the product GEMM / implicit-GEMM conv kernel: fused conv(+folded BN)+bias+SiLU/ReLU(+residual) and the FC layers as a
+// persistent, warp-specialised tcgen05 kernel (fp16 x fp16 -> fp32 in TMEM) with TMA-staged operands and a shared-memory staged,
+// TMA-stored epilogue.
 //
-// Replaces: the opaque conv stacks ONNXRuntime/TensorRT execute behind coreEngine.py:150-157 / :184-186 (same contract as
-// gemm_tc.cu, which stays in the tree only as the A/B baseline `ADAS_B200_GEMM=v2`).
+// Replaces: the opaque conv stacks ONNXRuntime/TensorRT execute behind coreEngine.py:150-157 (TensorRTEngine.engine_inference) /
+// :184-186 (OnnxEngine.engine_inference).
 //
-// What changed against v2 (profiles/r02_probe1_*: per-layer tables at real clocks):
-//   * 16 epilogue warps (four per TMEM lane quarter, 16-column batches): the 8-warp epilogue was latency-bound (+5.5 % whole net);
-//   * fp16 outputs leave through a 128-row x 64-column staging tile in shared memory (128-byte swizzle, conflict-free 16-byte
-//     st.shared) and ONE `cp.async.bulk.tensor` store per chunk (SASS: UTMASTG) instead of 32-byte per-lane row stores; rows
-//     of the zero halo are written as zeros, so the padded-NHWC invariant holds without per-row address arithmetic;
-//   * output-row / halo-mask arithmetic (two integer divisions per sub-tile) runs BEFORE the accumulator wait;
-//   * the TMEM accumulator stage is released right after the last tcgen05.ld of a tile, not after the math and the stores;
-//   * stage / phase counters are carried incrementally (no integer division per k-step in the producer and MMA loops);
-//   * stride-2 convs may use MT > 1 output patches per CTA tile (they share every weight tile), BN = 256 may use MT = 2
-//     (one 512-column accumulator set), and both are autotuned like the stride-1 layers;
-//   * per-device (not per-process) function attributes (advisor finding on gemm_tc.cu:976).
-// K order is (dy, k-block, dx) in every mode, as in v2, so results are bit-identical whatever tile shape is chosen.
+// Tile: BM = 128 output rows (pixels of the padded NHWC grid) x MT sub-tiles x BN output channels x BK = 64 channels per k-block.
+// A 3x3 stride-1 conv runs 9 taps x (Cin/64) k-blocks, each A tile being the SAME 2-D activation matrix loaded at row offset
+// m0 + dy*(W+2) + dx (the zero halo of the padded layout supplies the conv padding, TMA's out-of-bounds zero fill covers the matrix
+// ends); "slab" mode loads one 136-row slab per (dy, k-block) and points the three dx MMAs at row offsets 0/1/2 inside it;
+// stride-2 convs read 4-D boxes with traversal stride 2.  K order is (dy, k-block, dx) in every mode and for every tile shape, so
+// results are bit-identical whatever tile is chosen and whatever the batch size.
+//
+// Warp roles (576 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (warp-uniform loop, one
+// elected lane issues), warps 2..17 = epilogue (four per TMEM lane quarter, 16-column batches).  Persistent: grid = min(tiles, SMs),
+// two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Epilogue: tcgen05.ld -> +bias -> activation -> (+residual) -> fp16 -> 128-row x 64-column staging tile in shared memory (128-byte
+// swizzle, conflict-free 16-byte st.shared) -> ONE cp.async.bulk.tensor store per chunk (SASS: UTMASTG) through a 2-D map (dense
+// outputs) or a 4-D interior map (padded feature maps: halo rows are never written and stay zero).  The residual tile arrives by TMA
+// load into the same staging buffers two chunks ahead.  Output-row / halo-mask arithmetic runs BEFORE the accumulator wait
+// (multiply-shift divisors); the TMEM stage is released right after the last tcgen05.ld of a tile.  fp32 / transposed (FC swap-AB) /
+// BN % 64 != 0 outputs use direct per-lane stores.
+//
+// Function attributes and the SM count are per device (a process may hold engines on several GPUs).
 #include "common.h"
 #include <math.h>
 #include <stdlib.h>

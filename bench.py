@@ -327,7 +327,6 @@ def run_b200(args):
                                                          "dram_over_algorithmic", "all_kernels_dram_bytes_per_step", "gemm_launches_per_step", "source", "command")}
         except Exception:
             pass
-        cpu = cpu_baseline_sample(plans, frames=args.cpu_frames) if args.cpu_frames > 0 else None
         result = {
             "metric": "end-to-end frames/sec (YOLOv8l+UFLDv2+ByteTrack) 1280x720", "value": round(fps, 2), "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak",
@@ -356,11 +355,14 @@ def run_b200(args):
                          "algorithmic_gflop_per_step": round(gflop_step, 1),
                          "gemm_ms_per_step": round(ms_y + ms_u, 4), "all_plan_kernels_ms_per_step": round(ms_all_y + ms_all_u, 4)},
         }
+        # the CPU baseline runs with the pipeline shut down (its worker threads would compete for the host cores and bias the
+        # thread-count probe): same conditions as the --impl reference arm
+        pipe.close()
+        cpu = cpu_baseline_sample(plans, frames=args.cpu_frames) if args.cpu_frames > 0 else None
         if cpu is not None:
             result["cpu_baseline"] = cpu
         if world == 1 and args.other_configs:
             # BASELINE configs[1] / configs[2]: the two conv stacks alone at batch 32 (GEMM launches of one pass, timed like `roofline`)
-            pipe.close()
             other = {}
             for name, key, gf in (("yolov8l_b32 (configs[1])", "yolov8", gf_y), ("ufldv2_res34_b32 (configs[2])", "ufldv2", gf_u)):
                 eng = _capi.Engine(plans[key][0], local, max_batch=32)

@@ -1,4 +1,4 @@
-"""Time single conv layers (GEMM op only) through the engine: python tools/layer_bench.py"""
+"""Time single conv layers (GEMM op only) through the engine: python tools/layer_bench.py [substring of the layer name]"""
 import os, sys, tempfile
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np
@@ -16,7 +16,10 @@ LAYERS = [
     ("P4 3x3 256->256 40x40 B32", 32, 256, 256, 40, 40, 3),
 ]
 rng = np.random.default_rng(0)
+FILTER = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, B, cin, cout, H, W, k in LAYERS:
+    if FILTER not in name:
+        continue
     pb = plan.PlanBuilder(plan.MODEL_YOLOV5, 3, H, W)
     xin = pb.new_padded(H, W, cin)
     w = (rng.standard_normal((cout, cin, k, k)) * 0.05).astype(np.float32)

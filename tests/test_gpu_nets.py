@@ -289,7 +289,8 @@ def test_yolov5_lite_plan_matches_decoded_plan():
 
 @pytest.mark.parametrize("impl", ["native", "python"])
 def test_bytetracker_matches_reference_golden(golden_dir, impl):
-    from adas_b200.ObjectTracker import BYTETracker, BYTETrackerPy
+    from adas_b200.ObjectTracker import BYTETracker
+    from bytetrack_py import BYTETrackerPy
     g = np.load(os.path.join(golden_dir, "track.npz"))
     cls_ = BYTETracker if impl == "native" else BYTETrackerPy
     for seed, nobj in ((0, 8), (1, 14), (2, 4), (3, 25)):

@@ -1,1 +1,1 @@
-from .byteTrack.byteTracker import BYTETracker, BYTETrackerPy
+from .byteTrack.byteTracker import BYTETracker

@@ -14,8 +14,7 @@ DEVICE = 0
 def _tlbrs(tracks):
     if len(tracks) > 0 and isinstance(tracks[0], np.ndarray):
         return np.ascontiguousarray(tracks, dtype=float).reshape(-1, 4)
-    from .strack import STrack
-    return np.ascontiguousarray(STrack.multi_tlbr(tracks))
+    return np.ascontiguousarray([np.asarray(t.tlbr, dtype=float) for t in tracks], dtype=float).reshape(-1, 4)
 
 
 def iou_distance(atracks, btracks):

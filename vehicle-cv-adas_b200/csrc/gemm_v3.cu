@@ -244,7 +244,8 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // 32 bytes it is about to overwrite, and the finished chunk leaves through the TMA store.  Buffer reuse: R(j+2) targets the
         // buffer store S(j-1) read; the issuer waits for S(j-1) (`wait_group.read 1` right after committing S(j)) before issuing it.
         const bool res_tma = kTmaStore && g.res_tma;
-        auto buf_of = [&](uint32_t j) -> uint32_t { return res_tma ? j % V3_STG_BUFS : (j & 1u); };     // 2 buffers suffice without a residual
+        const bool stg3 = g.stg_bufs == V3_STG_BUFS;        // always with a residual; otherwise whenever the third buffer costs no pipeline stage
+        auto buf_of = [&](uint32_t j) -> uint32_t { return stg3 ? j % V3_STG_BUFS : (j & 1u); };
         int pf_w = blockIdx.x, pf_mt = 0, pf_cc = 0;
         uint32_t pf_j = 0;
         auto issue_res = [&]() {
@@ -401,10 +402,10 @@ conv_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         st_shared_v4(stg + ((((uint32_t)(2 * part)) ^ sw) << 4), o[0], o[1], o[2], o[3]);
                         st_shared_v4(stg + ((((uint32_t)(2 * part + 1)) ^ sw) << 4), o[4], o[5], o[6], o[7]);
                         fence_async_smem();                 // generic-proxy writes -> visible to the TMA (async proxy)
-                        if (issuer) { if (res_tma) bulk_wait_read1(); else bulk_wait_read0(); }      // see the protocol below
+                        if (issuer) { if (stg3) bulk_wait_read1(); else bulk_wait_read0(); }        // see the protocol below
                         __syncwarp();
                         asm volatile("bar.sync 1, 512;" ::: "memory");
-                        // Protocol (3 buffers, residual layers): chunk i fills buffer i % 3.  The issuer waits for all stores but the most recent
+                        // Protocol (3 buffers): chunk i fills buffer i % 3.  The issuer waits for all stores but the most recent
                         // one before it arrives at barrier(i); after barrier(i) every thread therefore knows stores <= i-2 are done, and the
                         // next write, into buffer (i+1) % 3 (last read by store i-2), is safe.  (2 buffers, no residual): the issuer waits for
                         // ALL earlier stores, so after barrier(i) stores <= i-1 are done and buffer (i+1) & 1 may be rewritten.
@@ -545,7 +546,11 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     static const int no_res_tma = env_int("ADAS_B200_NO_RES_TMA", 0);
     g->res_tma = (g->tma_st && p.res != nullptr && !no_res_tma && (reinterpret_cast<uintptr_t>(p.res) & 15u) == 0 &&
                   (p.res_ld < 0 ? -p.res_ld : p.res_ld) % 8 == 0) ? 1 : 0;
-    const int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? ((g->res_tma || p.chain) ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0);
+    // staging buffers: three with a residual (its prefetch protocol needs them) and in chain launches; otherwise three only where the
+    // third one does not cost an operand pipeline stage (decided below), else two
+    static const int force_stg2 = env_int("ADAS_B200_STG2", 0);
+    g->stg_bufs = (g->res_tma || p.chain) ? V3_STG_BUFS : 2;
+    int budget = V3_DYN_SMEM_MAX - 1024 - (g->tma_st ? g->stg_bufs * V3_STG_BYTES : 0);
     g->slab = 0;
     if (p.ntaps == 9 && !p.s2 && !no_slab) {
         const int slab_stage = g->MT * V3_SLAB_BYTES + 3 * b_bytes;
@@ -556,6 +561,10 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     int stages = budget / g->stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return 1;
+    if (g->tma_st && g->stg_bufs == 2 && !force_stg2) {
+        const int s3 = (budget - V3_STG_BYTES) / g->stage_bytes;
+        if ((s3 > 8 ? 8 : s3) == stages) g->stg_bufs = V3_STG_BUFS;
+    }
     g->stages = stages;
     g->p.stages = stages;
     g->stg_off = stages * g->stage_bytes;          // stage_bytes is a multiple of 1024
@@ -575,7 +584,7 @@ int gemm_v3_config(const GemmParams& p_in, GemmV3* g) {
     return 0;
 }
 
-static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? (g.res_tma ? V3_STG_BUFS : 2) * V3_STG_BYTES : 0) + 1024; }
+static int v3_smem_bytes(const GemmV3& g) { return g.stages * g.stage_bytes + (g.tma_st ? g.stg_bufs * V3_STG_BYTES : 0) + 1024; }
 
 int gemm_v3_launch(const GemmV3Launch& L, cudaStream_t st) {
     int num_sms = 0;
@@ -708,9 +717,9 @@ void gemm_v3_tile_of(const void* opaque, int* BN, int* MT) {
 bool gemm_v3_is_staged(const void* opaque) { return static_cast<const GemmV3Launch*>(opaque)->g.tma_st != 0; }
 void gemm_v3_describe(const void* opaque, char* out, int cap) {
     const GemmV3& g = static_cast<const GemmV3Launch*>(opaque)->g;
-    snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | v3 BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d tma_st=%d res_tma=%d", g.p.M,
+    snprintf(out, (size_t)cap, "M=%d N=%d K=%d taps=%d act=%d res=%d f32=%d s2=%d tr=%d | v3 BN=%d MT=%d slab=%d stages=%d acc=%d tiles=%d tma_st=%d res_tma=%d stg=%d", g.p.M,
              g.p.N, g.p.Kc * g.p.ntaps, g.p.ntaps, g.p.act, g.p.res ? (g.p.res_ld < 0 ? -1 : 1) : 0, g.p.out_f32, g.p.s2, g.p.transposed, g.p.BN, g.MT,
-             g.slab, g.stages, g.acc_stages, g.total_tiles, g.tma_st, g.res_tma);
+             g.slab, g.stages, g.acc_stages, g.total_tiles, g.tma_st, g.res_tma, g.tma_st ? g.stg_bufs : 0);
 }
 
 }  // namespace adas

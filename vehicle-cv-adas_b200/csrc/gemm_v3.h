@@ -23,6 +23,7 @@ struct GemmV3 {
     int a_sub_bytes, b_bytes, stage_bytes, stages;
     int n_tiles, m_tiles, total_tiles;
     int tma_st;        // staged TMA-store epilogue (fp16, not transposed, BN % 64 == 0)
+    int stg_bufs;      // staging buffers of that epilogue: 3 (one store may still be reading while the next chunk is written) or 2
     int res_tma;       // staged epilogue only: the residual tile of every chunk is fetched by TMA into the staging buffer
     int stg_off;       // byte offset of the two staging buffers behind the operand ring
     int pdl;

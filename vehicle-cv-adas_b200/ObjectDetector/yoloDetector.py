@@ -46,14 +46,15 @@ class YoloDetector(ObjectDetectBase):
         self.set_output_details(self.engine)
         # model_type <-> plan consistency (the reference trusts the user; a wrong pairing silently decodes boxes twice or never)
         kind, meta = self.engine.handle.model_kind, self.engine.handle.meta
-        want_v8 = self.model_type in (ObjectModelType.YOLOV8, ObjectModelType.YOLOV9)
+        # yoloDetector.py:114-124: YOLOv8 / v9 / v10 share the transposed [4 + nc, anchors] head layout; v5 / v6 / v7 the [anchors, 5 + nc] one
+        want_v8 = self.model_type in (ObjectModelType.YOLOV8, ObjectModelType.YOLOV9, ObjectModelType.YOLOV10)
         if want_v8 != (kind == 0):
             raise Exception(f"model_type {self.model_type} does not match the plan (kind {kind})")
         is_lite = kind == 1 and meta[2] != 0
         if (self.model_type == ObjectModelType.YOLOV5_LITE) != is_lite:
             raise Exception(f"model_type {self.model_type} needs a {'lite ' if not is_lite else 'non-lite '}YOLOv5 plan (plan.build_yolov5(lite=...))")
-        if self.model_type in (ObjectModelType.YOLOV10, ObjectModelType.EfficientDet):
-            raise Exception(f"{self.model_type} heads are not packed by adas_b200.plan")
+        if self.model_type == ObjectModelType.EfficientDet:
+            raise Exception("EfficientDet is a different detector class in the reference (efficientdetDetector.py); not provided here")
 
     def _initialize_class(self, classes_path) -> None:
         if classes_path is None:      # synthetic runs: COCO-sized anonymous label list

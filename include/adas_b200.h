@@ -161,6 +161,15 @@ int adas_lane_geometry(int device, const int32_t* pts, const int32_t* npts, cons
 int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h,
                             int32_t* area, int cap_area, int32_t* bird, adas_lane_geom* out);
 
+/* cv2.warpPerspective(frame, M, (out_w, out_h), flags=cv2.INTER_LINEAR) for a batch of BGR u8 frames, bit-exact (constant black
+ * border): PerspectiveTransformation.transformToBirdView / transformToFrontalView (perspectiveTransformation.py:90-117).
+ * M: [batch,9] row-major float64 forward matrices (the function inverts them as cv2 does); out: [batch,out_h,out_w,3]. */
+int adas_warp_perspective(int device, const uint8_t* frames_host, int batch, int H, int W, const double* M, int out_h, int out_w,
+                          uint8_t* out_host);
+/* Same, on the frames the engine's last detect call processed (still on the device: staged by the call, or the caller's device
+ * pointer when it passed frames_on_device = 1 and has not overwritten them). */
+int adas_engine_warp_perspective(adas_engine* e, int batch, const double* M, int out_h, int out_w, uint8_t* out_host);
+
 /* UFLD pre-processing alone (row H): u8 BGR host -> fp32 NCHW host [batch,3,in_h,in_w] */
 int adas_ufld_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W,
                          int in_h, int in_w, double crop_ratio, float* blob_nchw_host);

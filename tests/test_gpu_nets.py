@@ -615,3 +615,15 @@ def test_lane_geometry_from_resident_points_equals_standalone_call():
     with pytest.raises(Exception):
         _capi.Engine(path, 0, max_batch=1).lane_geometry(1, (1280, 720))       # no lane detect has run on that engine
     eng.close()
+
+
+def test_bird_view_of_resident_frames_equals_standalone_warp():
+    """adas_engine_warp_perspective warps the frames the last detect call left on the device (no second upload)."""
+    from adas_b200.TrafficLaneDetector.ufldDetector.perspectiveTransformation import PerspectiveTransformation
+    path, _, _ = cached_plan("ufldv2", backbone="18", cfg="culane")
+    eng = _capi.Engine(path, 0, max_batch=2)
+    frames = np.stack([synth.frame(s) for s in (5, 6)])
+    eng.ufld_detect(frames)
+    M = PerspectiveTransformation((1280, 720)).M
+    assert np.array_equal(eng.warp_perspective(2, M, (1280, 720)), _capi.warp_perspective(frames, M, (1280, 720)))
+    eng.close()

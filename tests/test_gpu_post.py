@@ -217,3 +217,30 @@ def test_birdview_points_and_curvature_on_device_match_reference_golden(golden_d
     pts, npts, status = _lanes_to_arrays([[[], synth.ego_lanes(100)[0], [], []]], [[0, 1, 0, 0]])
     r = _capi.lane_geometry(pts, npts, status, (1280, 720), M=Ms[0])[0]
     assert r["direction"] is None and r["curvature"] is None and r["offset"] is None and not r["area_status"] and len(r["area"]) == 0
+
+
+def test_warp_perspective_bit_exact_vs_reference_golden_and_cv2(golden_dir):
+    """transformToBirdView / transformToFrontalView on the device (csrc/warp.cu): every pixel equals cv2.warpPerspective's -- checked
+    against the hashes of the frames the reference class warped (tests/golden/birdview.npz, `_warp_sha`) and, where cv2 is importable,
+    against cv2 directly for other matrices, the inverse direction and a smaller frame."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "birdview.npz"))
+    cases = [(s, k) for s in range(8) for k in ("Default", "Top", "Bottom", None)]
+    frames = np.stack([synth.frame(seed) for seed, _ in cases])
+    Ms = np.stack([g[f"c{c}_M"] for c in range(len(cases))])
+    out = _capi.warp_perspective(frames, Ms, (1280, 720))
+    for c in range(len(cases)):
+        sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(out[c]).tobytes()).digest(), np.uint8)
+        assert np.array_equal(sha, g[f"c{c}_warp_sha"]), c
+    try:
+        import cv2
+    except Exception:
+        return
+    fr = np.stack([synth.frame(40 + i, 480, 640) for i in range(3)])
+    Ms = np.stack([g["c3_Minv"], g["c5_M"], np.array([[1.0, 0.1, -30.0], [0.02, 0.9, 12.5], [1e-4, -2e-4, 1.0]])])
+    for dsize in ((640, 480), (333, 97)):
+        got = _capi.warp_perspective(fr, Ms, dsize)
+        for b in range(3):
+            assert np.array_equal(got[b], cv2.warpPerspective(fr[b], Ms[b], dsize, flags=cv2.INTER_LINEAR)), (dsize, b)
+    with pytest.raises(Exception):
+        _capi.warp_perspective(fr[:1], np.zeros((3, 3)), (64, 64))          # singular matrix

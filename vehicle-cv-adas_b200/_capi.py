@@ -21,7 +21,7 @@ SYMBOLS = [
     "adas_last_error", "adas_version", "adas_launch_count", "adas_engine_create", "adas_engine_destroy",
     "adas_engine_model_kind", "adas_engine_meta", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
-    "adas_ufld_detect", "adas_ufld_postprocess", "adas_lane_geometry", "adas_ufld_lane_geometry", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
+    "adas_ufld_detect", "adas_ufld_postprocess", "adas_lane_geometry", "adas_ufld_lane_geometry", "adas_warp_perspective", "adas_engine_warp_perspective", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
     "adas_comm_unique_id", "adas_comm_create", "adas_comm_destroy", "adas_comm_all_gather", "adas_comm_sync", "adas_comm_read", "adas_comm_info",
@@ -248,6 +248,13 @@ class Engine:
                                      _p(counts, C.c_int32), _p(ncand, C.c_int32)))
         return boxes, scores, cls, idx, counts, ncand
 
+    def warp_perspective(self, batch: int, M, dsize) -> np.ndarray:
+        """bird view (cv2.warpPerspective, INTER_LINEAR) of the frames of the LAST detect call on this engine, from the device copy."""
+        Mb = as_c(np.broadcast_to(np.asarray(M, np.float64).reshape(-1, 3, 3), (batch, 3, 3)), np.float64)
+        out = np.empty((batch, dsize[1], dsize[0], 3), np.uint8)
+        check(lib().adas_engine_warp_perspective(self._h, batch, _p(Mb, C.c_double), dsize[1], dsize[0], _p(out, C.c_uint8)))
+        return out
+
     def lane_geometry(self, batch: int, img_wh, adjust_lanes: bool = False, M=None, bird_wh=(1280, 720)):
         """lane polygon / polyfit resampling / bird-view points / curvature + offset of the frames of the LAST ufld_detect (or
         detect_pair) on this engine, computed from the lane points still resident on the device."""
@@ -373,6 +380,17 @@ def _lane_geom_result(area, bird, out, have_M):
                     "direction": d, "curvature": float(o["curvature"]) if d is not None else None,
                     "offset": float(o["offset"]) if d is not None else None})
     return res
+
+
+def warp_perspective(frames: np.ndarray, M, dsize, device: int = 0) -> np.ndarray:
+    """cv2.warpPerspective(frame, M, dsize, flags=cv2.INTER_LINEAR) for uint8 [B,H,W,3] frames on the device, bit-exact.
+    M: one 3x3 matrix for all frames or [B,3,3]; dsize = (width, height) as in cv2."""
+    frames = as_c(frames, np.uint8)
+    B, H, W = frames.shape[:3]
+    Mb = as_c(np.broadcast_to(np.asarray(M, np.float64).reshape(-1, 3, 3), (B, 3, 3)), np.float64)
+    out = np.empty((B, dsize[1], dsize[0], 3), np.uint8)
+    check(lib().adas_warp_perspective(device, _p(frames, C.c_uint8), B, H, W, _p(Mb, C.c_double), dsize[1], dsize[0], _p(out, C.c_uint8)))
+    return out
 
 
 def lane_geometry(pts, npts, status, img_wh, adjust_lanes: bool = False, M=None, bird_wh=(1280, 720), device: int = 0):

@@ -111,6 +111,8 @@ int launch_stempack(const __half* img, int B, int H, int W, __half* q, cudaStrea
 // lane_geom.cu: ego-lane polygon / polyfit resampling / bird-view points / curvature + offset, one block per frame
 int launch_lane_geom(const int32_t* pts, const int32_t* npts, const uint8_t* status, const double* M, int batch, int max_pts, int img_w, int img_h,
                      int adjust, int bird_w, int bird_h, int32_t* area, int cap_area, int32_t* bird, ::adas_lane_geom* out, cudaStream_t st);
+// warp.cu: cv2.warpPerspective (INTER_LINEAR, constant black border) of device-resident BGR frames
+int launch_warp_perspective(const uint8_t* d_src, int B, int H, int W, const double* M_host, double* d_Minv, uint8_t* d_dst, int oh, int ow, cudaStream_t st);
 // stem_conv.cu: k x k stride-2 conv of the padded C=4 image (warp-level MMA, no patch matrix)
 int stem_conv_supported(int Cout, int k, int pad);
 int launch_stem_conv_s2(const __half* img, int B, int H, int W, const __half* wq, const float* bias, int Cout, int k, int pad, int act,

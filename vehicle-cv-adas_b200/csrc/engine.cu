@@ -72,6 +72,8 @@ struct adas_engine {
     // staging
     float* d_input = nullptr;        // [max_batch, C, H, W] fp32
     uint8_t* d_frames = nullptr;     // [max_batch * frame_bytes]
+    const uint8_t* last_dfr = nullptr; int last_fb = 0, last_fh = 0, last_fw = 0;      // frames of the last detect call, on the device
+    uint8_t* d_warp = nullptr; size_t warp_cap = 0; double* d_warpM = nullptr;          // adas_engine_warp_perspective scratch
     size_t frames_cap = 0;
     float* d_raw = nullptr;          // decoded head tensor (YOLO) [max_batch, ...]
     size_t raw_per_img = 0;
@@ -814,6 +816,7 @@ int adas_engine_destroy(adas_engine* e) {
     for (auto& kv : e->programs) if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
     for (auto& b : e->dbufs) cudaFree(b.ptr);
     cudaFree(e->d_blob); cudaFree(e->d_input); cudaFree(e->d_frames); cudaFree(e->d_raw); cudaFree(e->d_lut);
+    cudaFree(e->d_warp); cudaFree(e->d_warpM);
     cudaFree(e->d_area); cudaFree(e->d_bird); cudaFree(e->d_geom); cudaFree(e->d_M);
     cudaFree(e->d_row_anchor); cudaFree(e->d_col_anchor); cudaFree(e->d_pts); cudaFree(e->d_npts); cudaFree(e->d_status); cudaFree(e->d_coords);
     if (e->ev_frames) cudaEventDestroy(e->ev_frames);
@@ -891,7 +894,8 @@ int adas_engine_infer(adas_engine* e, const float* input, int batch, float* cons
 int adas_engine_infer_dev(adas_engine* e, const float* input, int batch, float* const* outs) { return infer_common(e, input, batch, outs, true); }
 
 static int stage_frames(adas_engine* e, const uint8_t* frames, int on_device, int batch, int H, int W, const uint8_t** dptr) {
-    if (on_device) { *dptr = frames; return 0; }
+    e->last_fb = batch; e->last_fh = H; e->last_fw = W;
+    if (on_device) { *dptr = frames; e->last_dfr = frames; return 0; }
     const size_t bytes = (size_t)batch * H * W * 3;
     if (bytes > e->frames_cap) {
         if (e->d_frames) ADAS_CUDA(cudaFree(e->d_frames));
@@ -902,6 +906,7 @@ static int stage_frames(adas_engine* e, const uint8_t* frames, int on_device, in
     }
     ADAS_CUDA(cudaMemcpyAsync(e->d_frames, frames, bytes, cudaMemcpyHostToDevice, e->stream));
     *dptr = e->d_frames;
+    e->last_dfr = e->d_frames;
     return 0;
 }
 
@@ -1010,6 +1015,25 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     return 0;
 }
 
+int adas_engine_warp_perspective(adas_engine* e, int batch, const double* M, int out_h, int out_w, uint8_t* out_host) {
+    ADAS_CHECK(e != nullptr && M != nullptr && out_host != nullptr, "adas_engine_warp_perspective: null argument");
+    ADAS_CHECK(e->last_dfr != nullptr && batch >= 1 && batch <= e->last_fb, "adas_engine_warp_perspective: batch %d, but the last detect call on this engine processed %d frames",
+               batch, e->last_fb);
+    ADAS_CUDA(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)batch * out_h * out_w * 3;
+    if (bytes > e->warp_cap || e->d_warpM == nullptr) {
+        cudaFree(e->d_warp); cudaFree(e->d_warpM);
+        e->d_warp = nullptr; e->d_warpM = nullptr;
+        e->warp_cap = (size_t)e->max_batch * out_h * out_w * 3;
+        ADAS_CUDA(cudaMalloc(&e->d_warp, e->warp_cap));
+        ADAS_CUDA(cudaMalloc(&e->d_warpM, (size_t)e->max_batch * 72));
+    }
+    if (launch_warp_perspective(e->last_dfr, batch, e->last_fh, e->last_fw, M, e->d_warpM, e->d_warp, out_h, out_w, e->stream)) return 1;
+    ADAS_CUDA(cudaMemcpyAsync(out_host, e->d_warp, bytes, cudaMemcpyDeviceToHost, e->stream));
+    ADAS_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h, int32_t* area,
                             int cap_area, int32_t* bird, adas_lane_geom* out) {
     ADAS_CHECK(e != nullptr && e->hdr.model_kind == ADAS_MODEL_UFLDV2, "adas_ufld_lane_geometry needs a UFLDv2 engine");
@@ -1018,7 +1042,8 @@ int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int
     ADAS_CUDA(cudaSetDevice(e->device));
     const int mp = e->ufld_max_pts;
     if (e->d_geom == nullptr || e->geom_cap_area < cap_area) {
-        cudaFree(e->d_area); cudaFree(e->d_bird); cudaFree(e->d_geom); cudaFree(e->d_M);
+        cudaFree(e->d_warp); cudaFree(e->d_warpM);
+    cudaFree(e->d_area); cudaFree(e->d_bird); cudaFree(e->d_geom); cudaFree(e->d_M);
         e->d_area = nullptr; e->d_bird = nullptr; e->d_geom = nullptr; e->d_M = nullptr;
         ADAS_CUDA(cudaMalloc(&e->d_area, (size_t)e->max_batch * cap_area * 8));
         ADAS_CUDA(cudaMalloc(&e->d_bird, (size_t)e->max_batch * 4 * mp * 8));
@@ -1067,6 +1092,8 @@ int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames
         ADAS_CUDA(cudaStreamWaitEvent(ufld->stream, e->ev_frames, 0));
         frames = dfr;
     }
+    e->last_dfr = ufld->last_dfr = frames;
+    e->last_fb = ufld->last_fb = batch; e->last_fh = ufld->last_fh = H; e->last_fw = ufld->last_fw = W;
     const LetterboxGeom g = letterbox_geom(H, W, (int)e->hdr.in_h, (int)e->hdr.in_w);
     if (launch_yolo_pre(frames, batch, g, static_cast<__half*>(e->dbufs[0].ptr), (int)e->bufs[0].C, nullptr, e->stream)) return 1;
     {

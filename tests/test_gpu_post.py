@@ -244,3 +244,42 @@ def test_warp_perspective_bit_exact_vs_reference_golden_and_cv2(golden_dir):
             assert np.array_equal(got[b], cv2.warpPerspective(fr[b], Ms[b], dsize, flags=cv2.INTER_LINEAR)), (dsize, b)
     with pytest.raises(Exception):
         _capi.warp_perspective(fr[:1], np.zeros((3, 3)), (64, 64))          # singular matrix
+
+
+def test_tracker_batch_call_with_empty_and_ragged_frames_equals_per_frame_updates():
+    """adas_tracker_update_batch over ragged frames (0 detections, only low-score detections, many detections) == the same frames fed
+    one by one to adas_tracker_update: identical records; the global id counter is reset between the two runs."""
+    def frames_of(seed):
+        seq = []
+        for f, (boxes, scores, labels) in enumerate(synth.track_sequence(seed, frames=24, objects=10)):
+            b = np.asarray(boxes, np.float64).reshape(-1, 4)
+            s = np.asarray(scores, np.float64)
+            c = np.asarray([int(str(l)[5:]) for l in labels], np.int32)
+            if f in (0, 5, 6, 17):                        # empty frames (also the very first one)
+                b, s, c = b[:0], s[:0], c[:0]
+            elif f == 9:                                  # only low-score detections: stage 2 alone
+                s = np.minimum(s, 0.3)
+            seq.append((b, s, c))
+        return seq
+    seq = frames_of(4)
+    one = _capi.NativeTracker(0)
+    one.reset()
+    per_frame = [one.update(b, s, c) for b, s, c in seq]
+    bat = _capi.NativeTracker(0)
+    bat.reset()
+    got = []
+    for i in range(0, len(seq), 8):
+        chunk = seq[i:i + 8]
+        counts = [len(s) for _, s, _ in chunk]
+        recs = bat.update_batch(counts, np.concatenate([b for b, _, _ in chunk]), np.concatenate([s for _, s, _ in chunk]),
+                                np.concatenate([c for _, _, c in chunk]))
+        got.extend(recs)
+    assert len(got) == len(per_frame)
+    n_tracks = 0
+    for f, (a, b) in enumerate(zip(per_frame, got)):
+        assert len(a) == len(b), f
+        for name in a.dtype.names:
+            if name not in ("pad", "pad2"):
+                assert np.array_equal(a[name], b[name]), (f, name)
+        n_tracks += len(a)
+    assert n_tracks > 50

@@ -11,7 +11,19 @@
 
 struct adas_lane_geom;      // include/adas_b200.h
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost a few ns unless a tool (nsys / ncu) is attached
+
 namespace adas {
+
+// NVTX range for the host-side phases of the C-ABI calls (per-frame path: detect calls, plan replay, tracker update): they show up as
+// named spans in nsys / ncu timelines next to the kernels they enqueue.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 
 // ---- error plumbing -----------------------------------------------------------------------
 void set_error(const char* fmt, ...);

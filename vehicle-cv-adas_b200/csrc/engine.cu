@@ -485,6 +485,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
 
 // run the network for `batch` images already staged in buffer 0 (fp16 padded NHWC image)
 static int run_plan(adas_engine* e, int batch) {
+    NvtxRange nv(e->hdr.model_kind == ADAS_MODEL_UFLDV2 ? "plan:ufldv2" : "plan:yolo");
     auto it = e->programs.find(batch);
     if (it == e->programs.end()) {
         Program prog;
@@ -924,6 +925,7 @@ int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
         e->yp_max_det = max_det;
     }
     const uint8_t* dfr = nullptr;
+    NvtxRange nv("adas_yolo_detect");
     PhaseTrace tr(e->stream, "yolo_detect");
     if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
     tr.mark("h2d");
@@ -987,6 +989,7 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
     ADAS_CUDA(cudaSetDevice(e->device));
     const uint8_t* dfr = nullptr;
+    NvtxRange nv("adas_ufld_detect");
     PhaseTrace tr(e->stream, "ufld_detect");
     if (stage_frames(e, frames, frames_on_device, batch, H, W, &dfr)) return 1;
     tr.mark("h2d");
@@ -1065,6 +1068,7 @@ int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int
 int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames, int frames_on_device, int batch, int H, int W, double box_score,
                      double nms_iou, int max_det, float* boxes_xywh, float* scores, int32_t* class_ids, int32_t* cand_index, int32_t* counts,
                      int32_t* n_candidates, int32_t* pts, int32_t* npts, uint8_t* status) {
+    NvtxRange nv("adas_detect_pair");
     static int conc = -1;
     if (conc < 0) { const char* c = getenv("ADAS_B200_CONCURRENT"); conc = (c && c[0] == '0') ? 0 : 1; }
     if (!conc || yolo->device != ufld->device) {

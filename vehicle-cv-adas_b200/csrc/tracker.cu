@@ -424,6 +424,7 @@ int adas_tracker_update_batch(adas_tracker* t, int n_frames, const int32_t* coun
                               const int32_t* class_ids, int max_out, adas_track* out, int32_t* n_out) {
     ADAS_CHECK(t != nullptr && n_frames >= 0 && counts != nullptr && n_out != nullptr, "adas_tracker_update_batch: bad arguments");
     ADAS_CUDA(cudaSetDevice(t->device));
+    adas::NvtxRange nv("adas_tracker_update_batch");
     size_t off = 0;
     const uint64_t t0 = adas::now_ns();
     for (int f = 0; f < n_frames; ++f) {

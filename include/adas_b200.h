@@ -34,7 +34,8 @@ enum { ADAS_MODEL_YOLOV8 = 0, ADAS_MODEL_YOLOV5 = 1, ADAS_MODEL_UFLDV2 = 2,
        /* adas_yolo_postprocess only: `raw` is the sigmoid-only head of a YOLOv5-lite export; YoloLiteParameters.lite_postprocess
         * (ObjectDetector/yoloDetector.py:36-50, model_type == ObjectModelType.YOLOV5_LITE) runs on the device first.  A lite PLAN
         * is a YOLOV5 plan whose header meta[2] != 0 (adas_engine_meta). */
-       ADAS_MODEL_YOLOV5_LITE = 3 };
+       ADAS_MODEL_YOLOV5_LITE = 3,
+       ADAS_MODEL_UFLDV1 = 4 };   /* UFLD v1 plans (ultrafastLaneDetector.py): one head tensor [griding_num + 1, rows, 4] */
 
 /* ---- errors ------------------------------------------------------------------------- */
 /* replaces: Python `raise Exception(...)` in coreEngine.py:12-14,20,26 */
@@ -169,6 +170,12 @@ int adas_warp_perspective(int device, const uint8_t* frames_host, int batch, int
 /* Same, on the frames the engine's last detect call processed (still on the device: staged by the call, or the caller's device
  * pointer when it passed frames_on_device = 1 and has not overwritten them). */
 int adas_engine_warp_perspective(adas_engine* e, int batch, const double* M, int out_h, int out_w, uint8_t* out_host);
+
+/* UFLD v1 decode only (UltrafastLaneDetector.__process_output, ultrafastLaneDetector.py:97-136): head [batch, (griding_num+1)*rows*4]
+ * fp32 host; cfg_w / cfg_h = ModelConfig.img_w / img_h, row_anchor[rows] in input-row coordinates.  pts [batch,4,rows,2]. */
+int adas_ufld_v1_postprocess(int device, const float* head_host, int batch, int griding_num, int rows, int in_w, int in_h, int cfg_w,
+                             int cfg_h, int img_w, int img_h, const double* row_anchor, int32_t* pts, int32_t* npts, uint8_t* status,
+                             double* coords_f);
 
 /* UFLD pre-processing alone (row H): u8 BGR host -> fp32 NCHW host [batch,3,in_h,in_w] */
 int adas_ufld_preprocess(int device, const uint8_t* frames_host, int batch, int H, int W,

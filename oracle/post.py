@@ -244,6 +244,49 @@ UFLD_ANCHORS = {"culane": (CULANE_ROW_ANCHOR, CULANE_COL_ANCHOR), "tusimple": (T
 
 
 # ---------------------------------------------------------------------------------------------
+# UFLD v1 decode
+# ---------------------------------------------------------------------------------------------
+# ModelConfig of ultrafastLaneDetector.py:15-37: source geometry, grid cells, row anchors (in 288-row input coordinates)
+UFLD_V1 = {
+    "tusimple": dict(img_w=1280, img_h=720, griding_num=100, cls_num_per_lane=56, row_anchor=np.linspace(64, 284, 56)),
+    "culane": dict(img_w=1640, img_h=590, griding_num=200, cls_num_per_lane=18, row_anchor=[round(v) for v in np.linspace(121, 287, 18)]),
+}
+
+
+def ufld_v1_decode(output: np.ndarray, cfg: dict, input_w: int, input_h: int, image_w: int, image_h: int):
+    """UltrafastLaneDetector.__process_output (ultrafastLaneDetector.py:97-136) for one frame: `output` [griding_num+1, rows, 4]
+    float32.  Rows are reversed, softmax (float32, as scipy.special.softmax computes it) over the grid cells without the last
+    "no lane" bin, expectation with 1-based cell indices (float64), 0 where the argmax is the "no lane" bin; a lane is detected when
+    more than two rows are non-zero.  Returns (points: 4 lists of [x, y] ints, status: 4 bools, loc: [rows, 4] float64)."""
+    out = np.asarray(output, np.float32)
+    out = out[:, ::-1, :]
+    x = out[:-1]
+    e = np.exp(x - np.amax(x, axis=0, keepdims=True))
+    prob = e / np.sum(e, axis=0, keepdims=True)
+    idx = (np.arange(cfg["griding_num"]) + 1).reshape(-1, 1, 1)
+    loc = np.sum(prob * idx, axis=0)
+    loc[np.argmax(out, axis=0) == cfg["griding_num"]] = 0
+    col_sample = np.linspace(0, input_w - 1, cfg["griding_num"])
+    col_sample_w = col_sample[1] - col_sample[0]
+    h_ratio, w_ratio = image_h / cfg["img_h"], image_w / cfg["img_w"]
+    pts, status = [], []
+    R = cfg["cls_num_per_lane"]
+    for lane in range(loc.shape[1]):
+        lp = []
+        if np.sum(loc[:, lane] != 0) > 2:
+            status.append(True)
+            for p in range(loc.shape[0]):
+                if loc[p, lane] > 0:
+                    px = loc[p, lane] * col_sample_w * cfg["img_w"] / input_w - 1
+                    py = cfg["img_h"] * (cfg["row_anchor"][R - 1 - p] / input_h) - 1
+                    lp.append([int(px * w_ratio), int(py * h_ratio)])
+        else:
+            status.append(False)
+        pts.append(lp)
+    return pts, status, loc
+
+
+# ---------------------------------------------------------------------------------------------
 # ByteTrack association
 # ---------------------------------------------------------------------------------------------
 def ious(a: np.ndarray, b: np.ndarray) -> np.ndarray:

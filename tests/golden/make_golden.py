@@ -164,6 +164,33 @@ def gen_ufld_tusimple():
     print("ufld tusimple cases", [(k, v.shape) for k, v in res.items() if "lane" in k][:8])
 
 
+def gen_ufld_v1():
+    """UFLD v1 (ultrafastLaneDetector.py) through the reference's detector, TuSimple and CULane configs, canned head tensors."""
+    import TrafficLaneDetector.ufldDetector.ultrafastLaneDetector as v1mod
+    res = {}
+    holder = [None]
+    for name, mt, (G, R) in (("tusimple", LaneModelType.UFLD_TUSIMPLE, (100, 56)), ("culane", LaneModelType.UFLD_CULANE, (200, 18))):
+        v1mod.OnnxEngine = lambda p, G=G, R=R: ref_shims.FakeEngine([1, 3, 288, 800], [[1, G + 1, R, 4]], ["output"], lambda x: [holder[0]])
+        det = v1mod.UltrafastLaneDetector("fake.onnx", mt, None)
+        for seed, inval in ((0, ()), (1, (2,)), (2, (0, 3))):
+            holder[0] = synth.ufld_v1_head(seed, G, R, invalid_lanes=inval)
+            for (h, w) in ((720, 1280), (480, 640)) if seed == 0 else ((720, 1280),):
+                fr = synth.frame(seed, h, w)
+                # DetectFrame itself cannot run under numpy 2: it hands the object-array `lanes_detected` to
+                # LaneDetectBase.__update_lanes_status, whose `lanes_status != []` no longer broadcasts (core.py:145) -- the two
+                # stages under test are called directly (ultrafastLaneDetector.py:139-145 does exactly this sequence)
+                blob = det._UltrafastLaneDetector__prepare_input(fr)
+                out = det.engine.engine_inference(blob)
+                lanes, status = det._UltrafastLaneDetector__process_output(out, det.cfg)
+                key = f"{name}_s{seed}_{h}x{w}"
+                for l in range(4):
+                    res[f"{key}_lane{l}"] = np.array(lanes[l], np.int32).reshape(-1, 2)
+                res[key + "_status"] = np.array([bool(v) for v in status], np.uint8)
+                res[key + "_blob_sha"] = np.frombuffer(bytes.fromhex(sha(blob)), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "ufld_v1_post.npz"), **res)
+    print("ufld v1 cases", [(k, v.shape) for k, v in res.items() if "lane" in k][:6])
+
+
 def gen_track():
     res = {}
     for seed, nobj in ((0, 8), (1, 14), (2, 4), (3, 25)):
@@ -225,6 +252,19 @@ def gen_ufld_net_pin():
         d = [float((r[k] - v).abs().max()) for k, v in zip(("loc_row", "loc_col", "exist_row", "exist_col"), m)]
         out[f"res{bb}"] = {"max_abs_diff": d, "ref_abs_max": float(r["loc_row"].abs().max())}
         print("ufld net pin", bb, d)
+    # UFLD v1: the oracle's restated net vs the reference's own v1 parsingNet (exportLib/ultrafastLane/model.py)
+    from ultrafastLane.model import parsingNet as parsingNetV1
+    for ds, (G, R) in (("tusimple", (100, 56)), ("culane", (200, 18))):
+        W = plan.synth_weights("ufldv2", 0)
+        plan.build_ufldv1(W, "18", ds)
+        ref = parsingNetV1(size=(288, 800), pretrained=False, backbone="18", cls_dim=(G + 1, R, 4), use_aux=False).eval()
+        nets.load_numpy_state_dict(ref, W.state_dict)
+        mine = nets.build("ufldv1", W.state_dict, backbone="18", griding_num=G, cls_num_per_lane=R)
+        x = torch.from_numpy(np.random.default_rng(5).standard_normal((1, 3, 288, 800)).astype(np.float32))
+        with torch.no_grad():
+            d = float((ref(x) - mine(x)).abs().max())
+        out[f"v1_res18_{ds}"] = {"max_abs_diff": [d], "ref_abs_max": float(ref(x).abs().max())}
+        print("ufld v1 net pin", ds, d)
     json.dump(out, open(os.path.join(OUT, "ufld_net_pin.json"), "w"), indent=1)
 
 
@@ -259,6 +299,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lite":
         gen_yolo_lite()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ufldv1":
+        gen_ufld_v1()
+        gen_ufld_net_pin()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tusimple":
         gen_ufld_tusimple()
         sys.exit(0)
@@ -267,6 +311,7 @@ if __name__ == "__main__":
     gen_yolo_lite()
     gen_ufld()
     gen_ufld_tusimple()
+    gen_ufld_v1()
     gen_track()
     gen_ufld_net_pin()
     gen_birdview()

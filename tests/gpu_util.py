@@ -31,15 +31,17 @@ def cached_plan(kind: str, seed: int = 0, **kw):
     """Build (once per process tree) the synthetic plan + return (path, Weights-like state_dict)."""
     CACHE = plan.cache_dir()
     import zlib
-    prof = zlib.crc32(repr((plan.SYNTH_PROFILES.get(kind), plan.PLAN_VERSION)).encode()) & 0xffff      # a changed operating point is a new plan
+    prof = zlib.crc32(repr((plan.SYNTH_PROFILES.get("ufldv2" if kind == "ufldv1" else kind), plan.PLAN_VERSION)).encode()) & 0xffff      # a changed operating point is a new plan
     tag = kind + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items())) + f"_s{seed}_{prof:04x}"
     path = os.path.join(CACHE, tag + ".b200w")
     variant = kw.get("scale", kw.get("backbone"))             # calibrated BatchNorm statistics exist for the tested variants
-    W = plan.synth_weights(kind, seed, variant=variant)
+    W = plan.synth_weights("ufldv2" if kind == "ufldv1" else kind, seed, variant=variant)
     if kind == "yolov8":
         pb = plan.build_yolov8(W, **kw)
     elif kind == "yolov5":
         pb = plan.build_yolov5(W, **kw)
+    elif kind == "ufldv1":
+        pb = plan.build_ufldv1(W, **kw)
     else:
         pb = plan.build_ufldv2(W, **kw)
     if not os.path.isfile(path):

@@ -101,6 +101,21 @@ def ufld_heads(seed: int, ngr=200, ncr=72, ngc=100, ncc=81, nl=4, invalid_lanes=
     return [loc_row, loc_col, ex_row, ex_col]
 
 
+def ufld_v1_head(seed: int, griding: int = 100, rows: int = 56, invalid_lanes=()):
+    """UFLD v1 output [1, griding+1, rows, 4] float32: a smooth ridge per lane, the last ("no lane") bin winning on some rows, an
+    exact tie between the ridge and the no-lane bin (argmax -> first = the ridge), lanes in `invalid_lanes` mostly empty."""
+    rng = np.random.default_rng(seed)
+    out = rng.normal(0, 2, (1, griding + 1, rows, 4)).astype(np.float32)
+    for l in range(4):
+        ridge = np.clip((np.linspace(0.15, 0.85, rows) + 0.07 * l) * griding, 0, griding - 1).astype(int)
+        ridge[:2] = (0, griding - 1)
+        out[0, ridge, np.arange(rows), l] += 10
+        none = rng.random(rows) < (0.95 if l in invalid_lanes else 0.15)
+        out[0, griding, none, l] += 25
+        out[0, griding, 7, l] = out[0, :griding, 7, l].max()          # tie with the ridge: argmax keeps the lower index
+    return out
+
+
 def nms_case(seed: int, n: int):
     """xywh float32 boxes + float64 confs with heavy overlap."""
     rng = np.random.default_rng(seed)

@@ -627,3 +627,67 @@ def test_bird_view_of_resident_frames_equals_standalone_warp():
     M = PerspectiveTransformation((1280, 720)).M
     assert np.array_equal(eng.warp_perspective(2, M, (1280, 720)), _capi.warp_perspective(frames, M, (1280, 720)))
     eng.close()
+
+
+@pytest.mark.parametrize("ds", ["tusimple", "culane"])
+def test_ufld_v1_engine_vs_oracle(ds):
+    """UFLD v1 (ultrafastLaneDetector.py + exportLib/ultrafastLane/model.py) end to end: pre-processing blob bit-exact, head tensor
+    vs the fp32 oracle (pinned to the reference's own parsingNet, tests/golden/ufld_net_pin.json), fused lane detect == the
+    reference decode applied to the device's own head, lane x-coordinates vs the oracle within 1e-3 of the source width on decisive
+    rows, and the UltrafastLaneDetector wrapper."""
+    from adas_b200.TrafficLaneDetector import UltrafastLaneDetector
+    from adas_b200.TrafficLaneDetector.ufldDetector.utils import LaneModelType
+    cfg = post.UFLD_V1[ds]
+    G, R = cfg["griding_num"], cfg["cls_num_per_lane"]
+    path, sd, _ = cached_plan("ufldv1", backbone="18", cfg=ds)
+    eng = _capi.Engine(path, 0, max_batch=2)
+    assert eng.model_kind == 4 and eng.output_shapes == [[1, G + 1, R, 4]]
+    frames = np.stack([synth.frame(s) for s in (0, 1)])
+    x = _capi.ufld_preprocess(frames, (288, 800), 1.0)
+    for b in range(2):
+        assert np.array_equal(x[b], post.ufld_prepare_input(frames[b], 288, 800, 1.0)[0])
+    out = eng.infer(x)[0]
+    model = nets.build("ufldv1", sd, backbone="18", griding_num=G, cls_num_per_lane=R)
+    with torch.no_grad():
+        ref = model(torch.from_numpy(x)).numpy()
+    assert out.shape == ref.shape == (2, G + 1, R, 4)
+    assert _report(f"ufld v1 {ds} head", out, ref) / max(1.0, float(np.abs(ref).max())) < 5e-3
+    pts, npts, status, coords = eng.ufld_detect(frames, want_coords=True)
+    n_cmp = n_skip = 0
+    for b in range(2):
+        # fused detect == reference decode applied to the device's own head
+        opts, ost, _ = post.ufld_v1_decode(out[b], cfg, 800, 288, 1280, 720)
+        assert [bool(v) for v in status[b]] == ost
+        for l in range(4):
+            n = int(npts[b, l])
+            assert n == len(opts[l])
+            diff = pts[b, l, :n] - np.array(opts[l], np.int32).reshape(-1, 2)
+            for j in np.nonzero(diff.any(axis=1))[0]:
+                assert np.abs(diff[j]).max() == 1 and abs(coords[b, l, j] - round(coords[b, l, j])) < 1e-3
+        # against the fp32 oracle: rows whose "no lane" decision and grid argmax are decisive
+        rpts, rst, rloc = post.ufld_v1_decode(ref[b], cfg, 800, 288, 1280, 720)
+        _, _, gloc = post.ufld_v1_decode(out[b], cfg, 800, 288, 1280, 720)
+        rr = ref[b][:, ::-1, :]
+        for l in range(4):
+            for p in range(R):
+                top = np.sort(rr[:G, p, l])[-2:]
+                decisive = abs(float(rr[G, p, l] - top[1])) > 5e-2 and float(top[1] - top[0]) > 5e-2
+                if not decisive:
+                    n_skip += 1
+                    continue
+                assert (rloc[p, l] == 0) == (gloc[p, l] == 0), (b, l, p)
+                if rloc[p, l] != 0:
+                    # loc is in grid cells; x = loc * (799 / (G - 1)) * img_w / 800 source pixels
+                    scale = (799.0 / (G - 1)) * cfg["img_w"] / 800.0 * (1280 / cfg["img_w"])
+                    assert abs(rloc[p, l] - gloc[p, l]) * scale <= 1e-3 * 1280, (b, l, p, rloc[p, l], gloc[p, l])
+                    n_cmp += 1
+    print(f"[parity] ufld v1 {ds}: {n_cmp} row anchors within 1e-3 of the width, {n_skip} skipped as indecisive; status {status.tolist()}")
+    assert n_cmp > 50
+    eng.close()
+    det = UltrafastLaneDetector(path, LaneModelType.UFLD_TUSIMPLE if ds == "tusimple" else LaneModelType.UFLD_CULANE, None, device=0)
+    det.DetectFrame(frames[0], adjust_lanes=False)
+    for l in range(4):
+        assert np.array_equal(np.array(det.lane_info.lanes_points[l], np.int32).reshape(-1, 2), pts[0, l, :int(npts[0, l])])
+    assert det.lane_info.lanes_status == [bool(v) for v in status[0]]
+    with pytest.raises(Exception):
+        UltrafastLaneDetector(path, LaneModelType.UFLD_CULANE if ds == "tusimple" else LaneModelType.UFLD_TUSIMPLE, None, device=0)

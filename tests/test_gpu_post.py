@@ -283,3 +283,25 @@ def test_tracker_batch_call_with_empty_and_ragged_frames_equals_per_frame_update
                 assert np.array_equal(a[name], b[name]), (f, name)
         n_tracks += len(a)
     assert n_tracks > 50
+
+
+@pytest.mark.parametrize("ds,G,R", [("tusimple", 100, 56), ("culane", 200, 18)])
+def test_ufld_v1_post_matches_reference_golden(golden_dir, ds, G, R):
+    """UFLD v1 decode on the device (ufld_v1_post_kernel) against the reference detector's own points / status
+    (tests/golden/ufld_v1_post.npz), both dataset geometries, two frame sizes."""
+    g = np.load(os.path.join(golden_dir, "ufld_v1_post.npz"))
+    cfg = post.UFLD_V1[ds]
+    for (h, w), cases in (((720, 1280), ((0, ()), (1, (2,)), (2, (0, 3)))), ((480, 640), ((0, ()),))):
+        head = np.concatenate([synth.ufld_v1_head(s, G, R, invalid_lanes=iv) for s, iv in cases])
+        pts, npts, status, coords = _capi.ufld_v1_postprocess(head, G, R, (800, 288), (cfg["img_w"], cfg["img_h"]), (w, h), np.asarray(cfg["row_anchor"], np.float64))
+        for b, (s, iv) in enumerate(cases):
+            key = f"{ds}_s{s}_{h}x{w}"
+            assert np.array_equal(status[b], g[key + "_status"]), key
+            for l in range(4):
+                gold = g[f"{key}_lane{l}"]
+                n = int(npts[b, l])
+                assert n == len(gold), (key, l)
+                diff = pts[b, l, :n] - gold
+                # numpy's float32 exp vs CUDA expf may differ in the last ulp: +-1 px only where the float64 x sits on an integer
+                for j in np.nonzero(diff.any(axis=1))[0]:
+                    assert np.abs(diff[j]).max() == 1 and abs(coords[b, l, j] - round(coords[b, l, j])) < 1e-3, (key, l, j)

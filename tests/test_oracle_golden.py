@@ -78,6 +78,20 @@ def test_ufld_tusimple_post_matches_reference(golden_dir, key):
     assert np.array_equal(_sha(blob), g[key + "_blob_sha"])
 
 
+@pytest.mark.parametrize("ds,G,R", [("tusimple", 100, 56), ("culane", 200, 18)])
+def test_ufld_v1_post_matches_reference(golden_dir, ds, G, R):
+    """UFLD v1 decode (ultrafastLaneDetector.py:97-136) and pre-processing (80-95) against the reference detector's own outputs."""
+    g = np.load(os.path.join(golden_dir, "ufld_v1_post.npz"))
+    for seed, inval in ((0, ()), (1, (2,)), (2, (0, 3))):
+        for (h, w) in ((720, 1280), (480, 640)) if seed == 0 else ((720, 1280),):
+            key = f"{ds}_s{seed}_{h}x{w}"
+            pts, status, _ = post.ufld_v1_decode(synth.ufld_v1_head(seed, G, R, invalid_lanes=inval)[0], post.UFLD_V1[ds], 800, 288, w, h)
+            for l in range(4):
+                assert np.array_equal(np.array(pts[l], np.int32).reshape(-1, 2), g[f"{key}_lane{l}"]), (key, l)
+            assert np.array_equal(np.array(status, np.uint8), g[key + "_status"]), key
+            assert np.array_equal(_sha(post.ufld_prepare_input(synth.frame(seed, h, w), 288, 800, 1.0)), g[key + "_blob_sha"]), key
+
+
 def test_association_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "track.npz"))
     for k in range(7):

@@ -101,6 +101,18 @@ def test_tusimple_plan_geometry():
     assert plan.build_ufldv2(plan.synth_weights("ufldv2", 0), "34").meta[6] == 0  # CULane
 
 
+def test_ufld_v1_plan_geometry():
+    """UFLD v1 (exportLib/ultrafastLane/model.py): 288x800 input, Linear(1800, 2048), head [griding_num + 1, rows, 4], keys cls.0 / cls.2."""
+    for ds, G, R in (("tusimple", 100, 56), ("culane", 200, 18)):
+        W = plan.synth_weights("ufldv2", 0)
+        pb = plan.build_ufldv1(W, "18", ds)
+        assert pb.model_kind == plan.MODEL_UFLDV1 and (pb.in_h, pb.in_w) == (288, 800)
+        assert pb.meta[:7] == [G, R, 0, 0, 4, (G + 1) * R * 4, 1 if ds == "tusimple" else 0]
+        assert "cls.0.weight" in W.state_dict and W.state_dict["cls.0.weight"].shape == (2048, 1800) and "cls.1.weight" not in W.state_dict
+        assert W.state_dict["cls.2.weight"].shape == ((G + 1) * R * 4, 2048)
+        assert not any(op[0] == plan.OP_LAYERNORM for op in pb.ops)
+
+
 def _corrupt(raw: bytes, off: int, fmt: str, value) -> bytes:
     b = bytearray(raw)
     struct.pack_into(fmt, b, off, value)

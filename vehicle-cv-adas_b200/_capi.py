@@ -21,7 +21,7 @@ SYMBOLS = [
     "adas_last_error", "adas_version", "adas_launch_count", "adas_engine_create", "adas_engine_destroy",
     "adas_engine_model_kind", "adas_engine_meta", "adas_engine_input_shape", "adas_engine_num_outputs", "adas_engine_output_shape",
     "adas_engine_infer", "adas_engine_infer_dev", "adas_yolo_detect", "adas_yolo_postprocess", "adas_yolo_preprocess",
-    "adas_ufld_detect", "adas_ufld_postprocess", "adas_lane_geometry", "adas_ufld_lane_geometry", "adas_warp_perspective", "adas_engine_warp_perspective", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
+    "adas_ufld_detect", "adas_ufld_postprocess", "adas_ufld_v1_postprocess", "adas_lane_geometry", "adas_ufld_lane_geometry", "adas_warp_perspective", "adas_engine_warp_perspective", "adas_ufld_preprocess", "adas_iou_cost", "adas_lap", "adas_associate",
     "adas_engine_stream", "adas_engine_num_buffers", "adas_engine_buffer_info", "adas_engine_write_buffer", "adas_engine_read_buffer",
     "adas_engine_run", "adas_engine_event_record", "adas_event_elapsed_ms", "adas_engine_time_ops", "adas_engine_num_steps", "adas_engine_time_step", "adas_detect_pair",
     "adas_comm_unique_id", "adas_comm_create", "adas_comm_destroy", "adas_comm_all_gather", "adas_comm_sync", "adas_comm_read", "adas_comm_info",
@@ -248,6 +248,10 @@ class Engine:
                                      _p(counts, C.c_int32), _p(ncand, C.c_int32)))
         return boxes, scores, cls, idx, counts, ncand
 
+    def _ufld_max_pts(self) -> int:
+        """points per lane the lane decode can emit: max(row anchors, column anchors) for v2, rows for v1 (model kind 4)"""
+        return self.output_shapes[0][2] if self.model_kind == 4 else max(self.output_shapes[0][2], self.output_shapes[1][2])
+
     def warp_perspective(self, batch: int, M, dsize) -> np.ndarray:
         """bird view (cv2.warpPerspective, INTER_LINEAR) of the frames of the LAST detect call on this engine, from the device copy."""
         Mb = as_c(np.broadcast_to(np.asarray(M, np.float64).reshape(-1, 3, 3), (batch, 3, 3)), np.float64)
@@ -258,7 +262,7 @@ class Engine:
     def lane_geometry(self, batch: int, img_wh, adjust_lanes: bool = False, M=None, bird_wh=(1280, 720)):
         """lane polygon / polyfit resampling / bird-view points / curvature + offset of the frames of the LAST ufld_detect (or
         detect_pair) on this engine, computed from the lane points still resident on the device."""
-        mp = max(self.output_shapes[0][2], self.output_shapes[1][2])
+        mp = self._ufld_max_pts()
         cap, area, bird, out = _lane_geom_outputs(batch, mp, img_wh[1], adjust_lanes)
         Mb = None
         if M is not None:
@@ -275,7 +279,7 @@ class Engine:
             frames = as_c(frames, np.uint8)
             B, H, W = frames.shape[:3]
             fptr = _p(frames, C.c_uint8)
-        mp = max(self.output_shapes[0][2], self.output_shapes[1][2])
+        mp = self._ufld_max_pts()
         pts = np.empty((B, 4, mp, 2), np.int32)
         npts = np.empty((B, 4), np.int32)
         status = np.empty((B, 4), np.uint8)
@@ -300,7 +304,7 @@ def detect_pair(yolo: "Engine", ufld: "Engine", frames, box_score: float, nms_io
     idx = np.empty((B, max_det), np.int32)
     counts = np.empty((B,), np.int32)
     ncand = np.empty((B,), np.int32)
-    mp = max(ufld.output_shapes[0][2], ufld.output_shapes[1][2])
+    mp = ufld._ufld_max_pts()
     pts = np.empty((B, 4, mp, 2), np.int32)
     npts = np.empty((B, 4), np.int32)
     status = np.empty((B, 4), np.uint8)
@@ -406,6 +410,20 @@ def lane_geometry(pts, npts, status, img_wh, adjust_lanes: bool = False, M=None,
                                    1 if adjust_lanes else 0, _p(Mb, C.c_double) if Mb is not None else None, bird_wh[0], bird_wh[1],
                                    _p(area, C.c_int32), cap, _p(bird, C.c_int32), out.ctypes.data_as(C.c_void_p)))
     return _lane_geom_result(area, bird, out, Mb is not None)
+
+
+def ufld_v1_postprocess(head: np.ndarray, griding_num: int, rows: int, in_wh, cfg_wh, img_wh, row_anchor, device: int = 0):
+    """UFLD v1 decode of head tensors [B, griding_num+1, rows, 4] (see adas_ufld_v1_postprocess)."""
+    head = as_c(head, np.float32)
+    B = head.shape[0]
+    pts = np.empty((B, 4, rows, 2), np.int32)
+    npts = np.empty((B, 4), np.int32)
+    status = np.empty((B, 4), np.uint8)
+    coords = np.empty((B, 4, rows), np.float64)
+    ra = as_c(row_anchor, np.float64)
+    check(lib().adas_ufld_v1_postprocess(device, _p(head, C.c_float), B, griding_num, rows, in_wh[0], in_wh[1], cfg_wh[0], cfg_wh[1], img_wh[0], img_wh[1],
+                                         _p(ra, C.c_double), _p(pts, C.c_int32), _p(npts, C.c_int32), _p(status, C.c_uint8), _p(coords, C.c_double)))
+    return pts, npts, status, coords
 
 
 def iou_cost(a_list, b_list, scores_list=None, device: int = 0):

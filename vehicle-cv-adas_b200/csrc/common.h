@@ -169,6 +169,8 @@ int launch_yolo_post(const float* raw, int kind, int B, int A, int nc, const Let
 
 // ---- UFLD post-processing (ufld_post.cu) -----------------------------------------------------------
 struct UfldDims { int ngr, ncr, ngc, ncc, nl; };
+int launch_ufld_v1_post(const float* head, int ld, int B, int G, int R, int in_w, int in_h, int cfg_w, int cfg_h, int img_w, int img_h,
+                        const double* row_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords, int max_pts, cudaStream_t st);
 int launch_ufld_post(const float* heads, int ld, int B, UfldDims d, int img_w, int img_h, const double* row_anchor,
                      const double* col_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords,
                      int max_pts, cudaStream_t st);

@@ -99,6 +99,8 @@ namespace adas {
 static size_t elem_size(uint32_t dtype) { return dtype == 1 ? 4 : 2; }
 
 // ADAS_B200_TRACE=1: per-phase device time (CUDA events on the handle's stream) + host wall time of each detect call
+static inline bool is_ufld(uint32_t kind) { return kind == ADAS_MODEL_UFLDV2 || kind == ADAS_MODEL_UFLDV1; }
+
 struct PhaseTrace {
     static bool enabled() { static int v = -1; if (v < 0) { const char* t = getenv("ADAS_B200_TRACE"); v = (t && t[0] == '1') ? 1 : 0; } return v == 1; }
     cudaStream_t st; const char* name; cudaEvent_t ev[10]; const char* names[10]; int n = 0; double t0 = 0;
@@ -485,7 +487,7 @@ static int build_program(adas_engine* e, int batch, Program* prog) {
 
 // run the network for `batch` images already staged in buffer 0 (fp16 padded NHWC image)
 static int run_plan(adas_engine* e, int batch) {
-    NvtxRange nv(e->hdr.model_kind == ADAS_MODEL_UFLDV2 ? "plan:ufldv2" : "plan:yolo");
+    NvtxRange nv(is_ufld(e->hdr.model_kind) ? "plan:ufld" : "plan:yolo");
     auto it = e->programs.find(batch);
     if (it == e->programs.end()) {
         Program prog;
@@ -519,7 +521,7 @@ static int run_plan(adas_engine* e, int batch) {
 }
 
 static int head_decode(adas_engine* e, int batch) {
-    if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) return 0;   // heads are the raw FC output buffer
+    if (is_ufld(e->hdr.model_kind)) return 0;   // heads are the raw FC output buffer
     YoloLevel lv[3];
     ADAS_CHECK(e->outs.size() == 3, "YOLO plan must declare 3 output levels");
     for (int i = 0; i < 3; ++i) {
@@ -619,6 +621,19 @@ static const UfldDataset kUfldDatasets[] = {
     {0, "CULane",   320, 1600, 200, 72, 100, 81, 0.6, 0.42, 1.0, 1.0, 0.0, 1.0},        // init_culane_config (47-55)
     {1, "TuSimple", 320,  800, 100, 56, 100, 41, 0.8, 160.0, 710.0, 720.0, 0.0, 1.0},   // init_tusimple_config (31-37): linspace(160,710,56)/720
 };
+// UFLD v1 dataset geometry (ModelConfig, ultrafastLaneDetector.py:15-37): source size the points are expressed in, grid cells, rows,
+// row anchors in 288-row input coordinates (TuSimple: np.linspace(64, 284, 56); CULane: [round(v) for v in np.linspace(121, 287, 18)])
+struct UfldV1Dataset { int id; const char* name; int img_w, img_h, G, R; double r0, r1; bool rounded; };
+static const UfldV1Dataset kUfldV1Datasets[] = {
+    {0, "CULane", 1640, 590, 200, 18, 121.0, 287.0, true},
+    {1, "TuSimple", 1280, 720, 100, 56, 64.0, 284.0, false},
+};
+static const UfldV1Dataset* ufld_v1_dataset(const PlanHeader& h) {
+    for (const UfldV1Dataset& d : kUfldV1Datasets)
+        if ((int)h.meta[6] == d.id) return &d;
+    return nullptr;
+}
+
 static const UfldDataset* ufld_dataset(const PlanHeader& h) {
     for (const UfldDataset& d : kUfldDatasets)
         if ((int)h.meta[6] == d.id) return &d;
@@ -720,6 +735,11 @@ static int validate_plan(const adas_engine* e, uint64_t file_bytes, const char* 
         ADAS_CHECK((int)ngr == ds->ngr && (int)ncr == ds->ncr && (int)ngc == ds->ngc && (int)ncc == ds->ncc && (int)h.in_h == ds->in_h && (int)h.in_w == ds->in_w,
                    "plan %s: head %llux%llu / %llux%llu at %ux%u is not the %s geometry its header names", path, (unsigned long long)ngr, (unsigned long long)ncr,
                    (unsigned long long)ngc, (unsigned long long)ncc, h.in_h, h.in_w, ds->name);
+    } else if (h.model_kind == ADAS_MODEL_UFLDV1) {
+        const UfldV1Dataset* ds = ufld_v1_dataset(h);
+        ADAS_CHECK(ds != nullptr, "plan %s: unknown UFLD v1 dataset id %u (0 = CULane, 1 = TuSimple)", path, h.meta[6]);
+        ADAS_CHECK((int)h.meta[0] == ds->G && (int)h.meta[1] == ds->R && h.meta[4] == 4 && h.meta[5] == (uint64_t)(ds->G + 1) * ds->R * 4 && h.in_h == 288 && h.in_w == 800,
+                   "plan %s: head %ux%u at %ux%u is not the UFLD v1 %s geometry its header names", path, h.meta[0], h.meta[1], h.in_h, h.in_w, ds->name);
     } else {
         ADAS_CHECK(h.model_kind == ADAS_MODEL_YOLOV8 || h.model_kind == ADAS_MODEL_YOLOV5, "plan %s: unknown model kind %u", path, h.model_kind);
         ADAS_CHECK(h.meta[0] >= 1 && h.meta[0] <= 1024 && h.meta[1] >= 1 && h.meta[1] <= (1u << 22), "plan %s: bad class / anchor counts", path);
@@ -779,7 +799,27 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     }
     const size_t in_elems = (size_t)e->hdr.in_c * e->hdr.in_h * e->hdr.in_w;
     ADAS_CUDA(cudaMalloc(&e->d_input, (size_t)max_batch * in_elems * 4));
-    if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) {
+    if (e->hdr.model_kind == ADAS_MODEL_UFLDV1) {
+        float lut[768];
+        ufld_lut_host(lut);
+        ADAS_CUDA(cudaMalloc(&e->d_lut, sizeof(lut)));
+        ADAS_CUDA(cudaMemcpy(e->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        const UfldV1Dataset* ds = ufld_v1_dataset(e->hdr);
+        const int R = ds->R;
+        e->ufld_max_pts = R;
+        e->ufld_crop = 1.0;                        // v1 resizes the whole frame to 800x288 (ultrafastLaneDetector.py:86)
+        std::vector<double> ra(R);
+        for (int i = 0; i < R; ++i) {
+            const double v = (i == R - 1) ? ds->r1 : ds->r0 + (double)i * ((ds->r1 - ds->r0) / (double)(R - 1));
+            ra[i] = ds->rounded ? nearbyint(v) : v;      // Python round(): half to even
+        }
+        ADAS_CUDA(cudaMalloc(&e->d_row_anchor, R * 8));
+        ADAS_CUDA(cudaMemcpy(e->d_row_anchor, ra.data(), R * 8, cudaMemcpyHostToDevice));
+        ADAS_CUDA(cudaMalloc(&e->d_pts, (size_t)max_batch * 4 * R * 2 * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_npts, (size_t)max_batch * 4 * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_status, (size_t)max_batch * 4));
+        ADAS_CUDA(cudaMalloc(&e->d_coords, (size_t)max_batch * 4 * R * 8));
+    } else if (e->hdr.model_kind == ADAS_MODEL_UFLDV2) {
         float lut[768];
         ufld_lut_host(lut);
         ADAS_CUDA(cudaMalloc(&e->d_lut, sizeof(lut)));
@@ -837,12 +877,13 @@ int adas_engine_input_shape(const adas_engine* e, int64_t s[4]) {
     s[0] = 1; s[1] = e->hdr.in_c; s[2] = e->hdr.in_h; s[3] = e->hdr.in_w;
     return 0;
 }
-int adas_engine_num_outputs(const adas_engine* e, int* n) { *n = e->hdr.model_kind == ADAS_MODEL_UFLDV2 ? 4 : 1; return 0; }
+int adas_engine_num_outputs(const adas_engine* e, int* n) { *n = e->hdr.model_kind == ADAS_MODEL_UFLDV2 ? 4 : 1; return 0; }     // UFLD v1: one tensor
 int adas_engine_output_shape(const adas_engine* e, int idx, int64_t s[4], int* rank) {
     const uint32_t* m = e->hdr.meta;
     s[0] = 1; s[1] = s[2] = s[3] = 0;
     if (e->hdr.model_kind == ADAS_MODEL_YOLOV8) { ADAS_CHECK(idx == 0, "bad output index"); s[1] = 4 + m[0]; s[2] = m[1]; *rank = 3; }
     else if (e->hdr.model_kind == ADAS_MODEL_YOLOV5) { ADAS_CHECK(idx == 0, "bad output index"); s[1] = m[1]; s[2] = 5 + m[0]; *rank = 3; }
+    else if (e->hdr.model_kind == ADAS_MODEL_UFLDV1) { ADAS_CHECK(idx == 0, "bad output index"); s[1] = m[0] + 1; s[2] = m[1]; s[3] = m[4]; *rank = 4; }   // [griding_num + 1, rows, lanes]
     else {
         ADAS_CHECK(idx >= 0 && idx < 4, "bad output index");
         *rank = 4;
@@ -884,6 +925,11 @@ static int infer_common(adas_engine* e, const float* input, int batch, float* co
             off += sz[k];
         }
         (void)total;
+    } else if (e->hdr.model_kind == ADAS_MODEL_UFLDV1) {
+        const PlanOutput& o = e->outs[0];
+        const float* src = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
+        const size_t total = e->hdr.meta[5], ld = e->bufs[o.buffer].C;
+        ADAS_CUDA(cudaMemcpy2DAsync(outs[0], total * 4, src, ld * 4, total * 4, batch, kind, e->stream));
     } else {
         ADAS_CUDA(cudaMemcpyAsync(outs[0], e->d_raw, (size_t)batch * e->raw_per_img * 4, kind, e->stream));
     }
@@ -915,7 +961,7 @@ int adas_yolo_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
                      double nms_iou, int max_det, float* boxes_xywh, float* scores, int32_t* class_ids, int32_t* cand_index,
                      int32_t* counts, int32_t* n_candidates) {
     ADAS_CHECK(e != nullptr, "null engine");
-    ADAS_CHECK(e->hdr.model_kind != ADAS_MODEL_UFLDV2, "adas_yolo_detect on a UFLD plan");
+    ADAS_CHECK(!is_ufld(e->hdr.model_kind), "adas_yolo_detect on a UFLD plan");
     ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
     ADAS_CUDA(cudaSetDevice(e->device));
     const int nc = (int)e->hdr.meta[0], A = (int)e->hdr.meta[1];
@@ -982,10 +1028,26 @@ int adas_yolo_preprocess(int device, const uint8_t* frames_host, int batch, int 
     return rc;
 }
 
+// lane decode of the head tensor(s) the plan just produced: v2 row / column anchors or the v1 grid expectation
+static int ufld_post_dispatch(adas_engine* e, int batch, int W, int H, bool want_coords) {
+    const uint32_t* m = e->hdr.meta;
+    const PlanOutput& o = e->outs[0];
+    const float* heads = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
+    const int mp = e->ufld_max_pts;
+    if (e->hdr.model_kind == ADAS_MODEL_UFLDV1) {
+        const UfldV1Dataset* ds = ufld_v1_dataset(e->hdr);
+        return launch_ufld_v1_post(heads, (int)e->bufs[o.buffer].C, batch, ds->G, ds->R, (int)e->hdr.in_w, (int)e->hdr.in_h, ds->img_w, ds->img_h, W, H,
+                                   e->d_row_anchor, e->d_pts, e->d_npts, e->d_status, want_coords ? e->d_coords : nullptr, mp, e->stream);
+    }
+    UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
+    return launch_ufld_post(heads, (int)e->bufs[o.buffer].C, batch, d, W, H, e->d_row_anchor, e->d_col_anchor, e->d_pts, e->d_npts, e->d_status,
+                            want_coords ? e->d_coords : nullptr, mp, e->stream);
+}
+
 int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device, int batch, int H, int W, int32_t* pts, int32_t* npts,
                      uint8_t* status, double* coords_f) {
     ADAS_CHECK(e != nullptr, "null engine");
-    ADAS_CHECK(e->hdr.model_kind == ADAS_MODEL_UFLDV2, "adas_ufld_detect on a YOLO plan");
+    ADAS_CHECK(is_ufld(e->hdr.model_kind), "adas_ufld_detect on a YOLO plan");
     ADAS_CHECK(batch >= 1 && batch <= e->max_batch, "batch %d outside [1, %d]", batch, e->max_batch);
     ADAS_CUDA(cudaSetDevice(e->device));
     const uint8_t* dfr = nullptr;
@@ -1000,13 +1062,8 @@ int adas_ufld_detect(adas_engine* e, const uint8_t* frames, int frames_on_device
     tr.mark("pre");
     if (run_plan(e, batch)) return 1;
     tr.mark("plan");
-    const uint32_t* m = e->hdr.meta;
-    UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
-    const PlanOutput& o = e->outs[0];
-    const float* heads = static_cast<const float*>(e->dbufs[o.buffer].ptr) + o.coff;
     const int mp = e->ufld_max_pts;
-    if (launch_ufld_post(heads, (int)e->bufs[o.buffer].C, batch, d, W, H, e->d_row_anchor, e->d_col_anchor, e->d_pts, e->d_npts, e->d_status,
-                         coords_f ? e->d_coords : nullptr, mp, e->stream)) return 1;
+    if (ufld_post_dispatch(e, batch, W, H, coords_f != nullptr)) return 1;
     ADAS_CUDA(cudaMemcpyAsync(pts, e->d_pts, (size_t)batch * 4 * mp * 2 * 4, cudaMemcpyDeviceToHost, e->stream));
     ADAS_CUDA(cudaMemcpyAsync(npts, e->d_npts, (size_t)batch * 4 * 4, cudaMemcpyDeviceToHost, e->stream));
     ADAS_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -1039,7 +1096,7 @@ int adas_engine_warp_perspective(adas_engine* e, int batch, const double* M, int
 
 int adas_ufld_lane_geometry(adas_engine* e, int batch, int img_w, int img_h, int adjust_lanes, const double* M, int bird_w, int bird_h, int32_t* area,
                             int cap_area, int32_t* bird, adas_lane_geom* out) {
-    ADAS_CHECK(e != nullptr && e->hdr.model_kind == ADAS_MODEL_UFLDV2, "adas_ufld_lane_geometry needs a UFLDv2 engine");
+    ADAS_CHECK(e != nullptr && is_ufld(e->hdr.model_kind), "adas_ufld_lane_geometry needs a UFLD engine");
     ADAS_CHECK(batch >= 1 && batch <= e->ufld_last_batch, "adas_ufld_lane_geometry: batch %d, but the last lane detect on this engine decoded %d frames", batch, e->ufld_last_batch);
     ADAS_CHECK(area != nullptr && out != nullptr && (M == nullptr || bird != nullptr), "adas_ufld_lane_geometry: null argument");
     ADAS_CUDA(cudaSetDevice(e->device));
@@ -1115,13 +1172,8 @@ int adas_detect_pair(adas_engine* yolo, adas_engine* ufld, const uint8_t* frames
     if (copy_yolo_results_enqueue(e->yp, batch, max_det, boxes_xywh, scores, class_ids, cand_index, counts, e->h_ncand.data(), e->stream)) return 1;
     {
         adas_engine* u = ufld;
-        const uint32_t* m = u->hdr.meta;
-        UfldDims d{(int)m[0], (int)m[1], (int)m[2], (int)m[3], (int)m[4]};
-        const PlanOutput& o = u->outs[0];
-        const float* heads = static_cast<const float*>(u->dbufs[o.buffer].ptr) + o.coff;
         const int mp = u->ufld_max_pts;
-        if (launch_ufld_post(heads, (int)u->bufs[o.buffer].C, batch, d, W, H, u->d_row_anchor, u->d_col_anchor, u->d_pts, u->d_npts, u->d_status, nullptr, mp,
-                             u->stream)) return 1;
+        if (ufld_post_dispatch(u, batch, W, H, false)) return 1;
         ADAS_CUDA(cudaMemcpyAsync(pts, u->d_pts, (size_t)batch * 4 * mp * 2 * 4, cudaMemcpyDeviceToHost, u->stream));
         ADAS_CUDA(cudaMemcpyAsync(npts, u->d_npts, (size_t)batch * 4 * 4, cudaMemcpyDeviceToHost, u->stream));
         ADAS_CUDA(cudaMemcpyAsync(status, u->d_status, (size_t)batch * 4, cudaMemcpyDeviceToHost, u->stream));
@@ -1155,6 +1207,28 @@ int adas_ufld_postprocess(int device, const float* heads_host, int batch, int ng
         if (ce != cudaSuccess) { set_error("ufld_postprocess D2H: %s", cudaGetErrorString(ce)); rc = 1; }
     }
     cudaFree(d_h); cudaFree(d_ra); cudaFree(d_ca); cudaFree(d_p); cudaFree(d_n); cudaFree(d_s); cudaFree(d_co);
+    return rc;
+}
+
+int adas_ufld_v1_postprocess(int device, const float* head_host, int batch, int griding_num, int rows, int in_w, int in_h, int cfg_w, int cfg_h, int img_w,
+                             int img_h, const double* row_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords_f) {
+    ADAS_CUDA(cudaSetDevice(device));
+    const size_t total = (size_t)(griding_num + 1) * rows * 4;
+    float* d_h = nullptr; double *d_ra = nullptr, *d_co = nullptr; int32_t *d_p = nullptr, *d_n = nullptr; uint8_t* d_s = nullptr;
+    ADAS_CUDA(cudaMalloc(&d_h, (size_t)batch * total * 4)); ADAS_CUDA(cudaMalloc(&d_ra, rows * 8));
+    ADAS_CUDA(cudaMalloc(&d_p, (size_t)batch * 4 * rows * 8)); ADAS_CUDA(cudaMalloc(&d_n, (size_t)batch * 16)); ADAS_CUDA(cudaMalloc(&d_s, (size_t)batch * 4));
+    ADAS_CUDA(cudaMalloc(&d_co, (size_t)batch * 4 * rows * 8));
+    ADAS_CUDA(cudaMemcpy(d_h, head_host, (size_t)batch * total * 4, cudaMemcpyHostToDevice));
+    ADAS_CUDA(cudaMemcpy(d_ra, row_anchor, rows * 8, cudaMemcpyHostToDevice));
+    int rc = launch_ufld_v1_post(d_h, (int)total, batch, griding_num, rows, in_w, in_h, cfg_w, cfg_h, img_w, img_h, d_ra, d_p, d_n, d_s, d_co, rows, 0);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpy(pts, d_p, (size_t)batch * 4 * rows * 8, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(npts, d_n, (size_t)batch * 16, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(status, d_s, (size_t)batch * 4, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && coords_f) ce = cudaMemcpy(coords_f, d_co, (size_t)batch * 4 * rows * 8, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { set_error("ufld_v1_postprocess D2H: %s", cudaGetErrorString(ce)); rc = 1; }
+    }
+    cudaFree(d_h); cudaFree(d_ra); cudaFree(d_p); cudaFree(d_n); cudaFree(d_s); cudaFree(d_co);
     return rc;
 }
 

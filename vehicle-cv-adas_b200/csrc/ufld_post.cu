@@ -107,4 +107,75 @@ int launch_ufld_post(const float* heads, int ld, int B, UfldDims d, int img_w, i
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// UFLD v1 decode: UltrafastLaneDetector.__process_output, TrafficLaneDetector/ufldDetector/ultrafastLaneDetector.py:97-136
+//   - rows reversed (`[:, ::-1, :]`); float32 softmax over the griding_num cells without the last "no lane" bin, computed the way
+//     scipy.special.softmax does (x - max, exp, sequential float32 sum along the grid axis, divide)                       :102-103
+//   - expectation sum(prob * (cell + 1)) in float64 (float32 prob x int64 index promotes), 0 where the argmax over all
+//     griding_num + 1 bins (first maximum) is the "no lane" bin                                                            :104-109
+//   - lane detected iff more than two rows are non-zero; points for rows with loc > 0:
+//       x = loc * col_sample_w * cfg.img_w / input_width - 1,  y = cfg.img_h * (row_anchor[R-1-p] / input_height) - 1,
+//       [int(x * w_ratio), int(y * h_ratio)]                                                                               :112-131
+// One CTA per frame, one thread per (reversed row p, lane l); head layout [griding_num + 1][rows][4].
+__global__ void __launch_bounds__(UFLD_THREADS)
+ufld_v1_post_kernel(const float* __restrict__ head, int ld, int G, int R, int in_w, int in_h, int cfg_w, int cfg_h, int img_w, int img_h,
+                    const double* __restrict__ row_anchor, int32_t* __restrict__ pts, int32_t* __restrict__ npts, uint8_t* __restrict__ status,
+                    double* __restrict__ coords, int max_pts) {
+    __shared__ double s_loc[4][UFLD_MAX_ANCH];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* out = head + (size_t)b * ld;
+    const int stride = R * 4;
+    for (int t = tid; t < R * 4; t += UFLD_THREADS) {
+        const int p = t / 4, l = t % 4;
+        const int r = R - 1 - p;                                   // reversed rows
+        const float* col = out + (size_t)r * 4 + l;
+        float mx = col[0];
+        for (int g = 1; g < G; ++g) mx = fmaxf(mx, col[(size_t)g * stride]);
+        const bool none = col[(size_t)G * stride] > mx;            // argmax over G + 1 bins is the last one only if it is strictly larger
+        float sum = 0.f;
+        for (int g = 0; g < G; ++g) sum = __fadd_rn(sum, expf(__fsub_rn(col[(size_t)g * stride], mx)));
+        double acc = 0.0;
+        for (int g = 0; g < G; ++g) {
+            const float pr = __fdiv_rn(expf(__fsub_rn(col[(size_t)g * stride], mx)), sum);
+            acc = __dadd_rn(acc, __dmul_rn((double)pr, (double)(g + 1)));
+        }
+        s_loc[l][p] = none ? 0.0 : acc;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        const int l = tid;
+        int nz = 0;
+        for (int p = 0; p < R; ++p) nz += s_loc[l][p] != 0.0;
+        int n = 0;
+        int32_t* o = pts + ((size_t)b * 4 + l) * max_pts * 2;
+        double* oc = coords ? coords + ((size_t)b * 4 + l) * max_pts : nullptr;
+        if (nz > 2) {
+            // col_sample = np.linspace(0, input_width - 1, griding_num): col_sample[1] - col_sample[0] = 1 * step + 0 - 0
+            const double csw = __ddiv_rn((double)(in_w - 1), (double)(G - 1));
+            const double w_ratio = __ddiv_rn((double)img_w, (double)cfg_w), h_ratio = __ddiv_rn((double)img_h, (double)cfg_h);
+            for (int p = 0; p < R; ++p) {
+                const double loc = s_loc[l][p];
+                if (!(loc > 0.0)) continue;
+                const double x = __dsub_rn(__ddiv_rn(__dmul_rn(__dmul_rn(loc, csw), (double)cfg_w), (double)in_w), 1.0);
+                const double y = __dsub_rn(__dmul_rn((double)cfg_h, __ddiv_rn(row_anchor[R - 1 - p], (double)in_h)), 1.0);
+                o[n * 2] = (int)__dmul_rn(x, w_ratio);
+                o[n * 2 + 1] = (int)__dmul_rn(y, h_ratio);
+                if (oc) oc[n] = __dmul_rn(x, w_ratio);
+                ++n;
+            }
+        }
+        npts[b * 4 + l] = n;
+        status[b * 4 + l] = nz > 2 ? 1 : 0;
+    }
+}
+
+int launch_ufld_v1_post(const float* head, int ld, int B, int G, int R, int in_w, int in_h, int cfg_w, int cfg_h, int img_w, int img_h,
+                        const double* row_anchor, int32_t* pts, int32_t* npts, uint8_t* status, double* coords, int max_pts, cudaStream_t st) {
+    ADAS_CHECK(G >= 3 && R >= 1 && R <= UFLD_MAX_ANCH && max_pts >= R, "ufld_v1_post: bad head %d x %d", G, R);
+    ufld_v1_post_kernel<<<B, UFLD_THREADS, 0, st>>>(head, ld, G, R, in_w, in_h, cfg_w, cfg_h, img_w, img_h, row_anchor, pts, npts, status, coords, max_pts);
+    count_launch();
+    ADAS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace adas

@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-MODEL_YOLOV8, MODEL_YOLOV5, MODEL_UFLDV2 = 0, 1, 2
+MODEL_YOLOV8, MODEL_YOLOV5, MODEL_UFLDV2, MODEL_UFLDV1 = 0, 1, 2, 4      # 3 = ADAS_MODEL_YOLOV5_LITE (post-processing kind only)
 OP_GEMM, OP_IM2COL, OP_MAXPOOL, OP_UPSAMPLE2X, OP_LAYERNORM, OP_STEMPACK, OP_STEMCONV = 1, 2, 3, 4, 5, 6, 7
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 PLAN_VERSION = 1
@@ -560,8 +560,17 @@ UFLD_CULANE = dict(num_grid_row=200, num_cls_row=72, num_grid_col=100, num_cls_c
 UFLD_TUSIMPLE = dict(num_grid_row=100, num_cls_row=56, num_grid_col=100, num_cls_col=41, num_lanes=4, in_h=320, in_w=800, fc_norm=False,
                      dataset=1, crop_ratio=0.8)
 UFLD_DATASETS = {"culane": UFLD_CULANE, "tusimple": UFLD_TUSIMPLE}
+# UFLD v1 (ultrafastLaneDetector.py:15-37 ModelConfig; exportLib/ultrafastLane/model.py): 288x800 input, one output tensor
+UFLD_V1_TUSIMPLE = dict(v1=True, griding_num=100, cls_num_per_lane=56, num_lanes=4, in_h=288, in_w=800, fc_norm=False, dataset=1, crop_ratio=1.0)
+UFLD_V1_CULANE = dict(v1=True, griding_num=200, cls_num_per_lane=18, num_lanes=4, in_h=288, in_w=800, fc_norm=False, dataset=0, crop_ratio=1.0)
+UFLD_V1_DATASETS = {"culane": UFLD_V1_CULANE, "tusimple": UFLD_V1_TUSIMPLE}
 BN_EPS_TV = 1e-5
 UFLD_STEM_DEFAULT = "pack"
+
+
+def build_ufldv1(weights: Weights, backbone: str = "18", cfg="tusimple") -> PlanBuilder:
+    """UFLD v1: the same ResNet trunk, pool conv and two FC layers as v2 without LayerNorm; head = [griding_num + 1, rows, 4]."""
+    return build_ufldv2(weights, backbone, UFLD_V1_DATASETS[cfg] if isinstance(cfg, str) else cfg)
 
 
 def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> PlanBuilder:
@@ -569,7 +578,8 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
         cfg = UFLD_DATASETS[cfg]
     blocks = {"18": [2, 2, 2, 2], "34": [3, 4, 6, 3]}[backbone]
     in_h, in_w = cfg["in_h"], cfg["in_w"]
-    pb = PlanBuilder(MODEL_UFLDV2, 3, in_h, in_w)
+    v1 = bool(cfg.get("v1"))
+    pb = PlanBuilder(MODEL_UFLDV1 if v1 else MODEL_UFLDV2, 3, in_h, in_w)
     W = weights
     w, b = W.conv_bn("model", 64, 3, 7, BN_EPS_TV, conv_key="conv1", bn_key="bn1")
     # stem: "pack" = re-layout pass + a 4-tap tcgen05 GEMM (stem7x7s2), "direct" = stem_conv.cu straight from the image
@@ -598,8 +608,13 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
     pool = pb.conv(x, wp, bp, 1, 1, ACT_NONE)
     fh, fw = pool.H, pool.W
     input_dim = fh * fw * 8                     # model_culane.py:23
-    ngr, ncr, ngc, ncc, nl = cfg["num_grid_row"], cfg["num_cls_row"], cfg["num_grid_col"], cfg["num_cls_col"], cfg["num_lanes"]
-    total_dim = ngr * ncr * nl + ngc * ncc * nl + 2 * ncr * nl + 2 * ncc * nl
+    if v1:       # UFLD v1 head (exportLib/ultrafastLane/model.py:20-66): one tensor [griding_num + 1, cls_num_per_lane, 4]
+        ngr, ncr, ngc, ncc, nl = cfg["griding_num"], cfg["cls_num_per_lane"], 0, 0, cfg["num_lanes"]
+        total_dim = (ngr + 1) * ncr * nl
+        assert input_dim == 1800, "UFLD v1 hard-codes Linear(1800, 2048) (model.py:62): 288x800 input"
+    else:
+        ngr, ncr, ngc, ncc, nl = cfg["num_grid_row"], cfg["num_cls_row"], cfg["num_grid_col"], cfg["num_cls_col"], cfg["num_lanes"]
+        total_dim = ngr * ncr * nl + ngc * ncc * nl + 2 * ncr * nl + 2 * ncc * nl
     mid = 2048
     # the flattened NCHW feature f = c*fh*fw + h*fw + w lives at j = ((h+1)*(fw+2) + (w+1))*8 + c of the padded slab
     slab = (fh + 2) * (fw + 2) * 8
@@ -611,11 +626,19 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
         be = W.get("cls.0.bias", (input_dim,), "ln_beta")
     else:
         g, be = None, None
-    w1 = W.get("cls.1.weight", (mid, input_dim), "linear")
-    b1 = W.get("cls.1.bias", (mid,), "bias")
-    w2 = W.get("cls.3.weight", (total_dim, mid), "linear")
-    b2 = W.get("cls.3.bias", (total_dim,), "bias")
-    exist_bias = None if W.real else W.profile.get("ufld_exist_bias")
+    # v2: cls = Sequential(LayerNorm | Identity, Linear, ReLU, Linear) -> cls.1 / cls.3; v1: Sequential(Linear, ReLU, Linear) -> cls.0 / cls.2
+    k1, k2 = ("cls.0", "cls.2") if v1 else ("cls.1", "cls.3")
+    w1 = W.get(k1 + ".weight", (mid, input_dim), "linear")
+    b1 = W.get(k1 + ".bias", (mid,), "bias")
+    w2 = W.get(k2 + ".weight", (total_dim, mid), "linear")
+    b2 = W.get(k2 + ".bias", (total_dim,), "bias")
+    exist_bias = None if (W.real or v1) else W.profile.get("ufld_exist_bias")
+    if v1 and not W.real and not getattr(W, "_ufld_v1_applied", False):
+        # synthetic operating point for v1: the "no lane" bin (last grid index) loses on most rows, so lanes are detected
+        b2 = b2.copy()
+        b2.reshape(ngr + 1, ncr, nl)[ngr] -= np.float32(2.0)
+        W.state_dict[k2 + ".bias"] = b2
+        W._ufld_v1_applied = True
     if exist_bias and not getattr(W, "_ufld_exist_applied", False):
         # synthetic operating point (see SYNTH_PROFILES): shift the "valid" planes of exist_row / exist_col, in the shared state_dict
         b2 = b2.copy()

@@ -634,10 +634,15 @@ def build_ufldv2(weights: Weights, backbone: str = "34", cfg=UFLD_CULANE) -> Pla
     b2 = W.get(k2 + ".bias", (total_dim,), "bias")
     exist_bias = None if (W.real or v1) else W.profile.get("ufld_exist_bias")
     if v1 and not W.real and not getattr(W, "_ufld_v1_applied", False):
-        # synthetic operating point for v1: the "no lane" bin (last grid index) loses on most rows, so lanes are detected
+        # synthetic operating point for v1: the "no lane" bin (last grid index) loses on most rows, so lanes are detected, and the
+        # head gain is halved -- the v1 coordinate is an expectation over ALL grid cells, so its fp16-vs-fp32 error scales with the
+        # logit scale of a random head (CPU fp16 emulation, tools/synth_operating_point.py style: gain 1 -> 8e-4 of the width,
+        # 0.5 -> 3e-4; trained heads are peaked and far less sensitive)
         b2 = b2.copy()
         b2.reshape(ngr + 1, ncr, nl)[ngr] -= np.float32(2.0)
+        w2 = (w2 * np.float32(0.5)).astype(np.float32)
         W.state_dict[k2 + ".bias"] = b2
+        W.state_dict[k2 + ".weight"] = w2
         W._ufld_v1_applied = True
     if exist_bias and not getattr(W, "_ufld_exist_applied", False):
         # synthetic operating point (see SYNTH_PROFILES): shift the "valid" planes of exist_row / exist_col, in the shared state_dict

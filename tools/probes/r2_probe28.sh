@@ -3,5 +3,5 @@
 O=gpurun_out/probe28; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -s -k "v1" > $O/pytest_v1.txt 2>&1; echo "v1 rc=$?"
 grep -E "passed|failed|^E  |FAILED|parity\]" $O/pytest_v1.txt | tail -n 14
-timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > $O/pytest_all.txt 2>&1; echo "all rc=$?"; tail -n 4 $O/pytest_all.txt
+true
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2

@@ -553,6 +553,7 @@ def test_two_devices_in_one_process():
         det = eng.yolo_detect(frames, 0.44, 0.45)
         lanes = ufl.ufld_detect(frames)
         trk = _capi.NativeTracker(device=dev, track_thresh=0.34)
+        trk.reset()                      # the id counter is process-global, as BaseTrack._count in the reference
         n = int(det[4][0])
         rec = trk.update(det[0][0, :n], det[1][0, :n], det[2][0, :n])
         res.append((raw, det, lanes, rec))

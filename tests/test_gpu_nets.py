@@ -563,7 +563,8 @@ def test_two_devices_in_one_process():
         assert np.array_equal(a, b)
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
-    assert np.array_equal(res[0][3], res[1][3])
+    for name in res[0][3].dtype.names:
+        assert np.array_equal(res[0][3][name], res[1][3][name]), name
 
 
 def test_engine_from_onnx_file_matches_state_dict_plan(tmp_path):

@@ -559,10 +559,17 @@ def test_two_devices_in_one_process():
         res.append((raw, det, lanes, rec))
         eng.close(); ufl.close()
     assert np.array_equal(res[0][0], res[1][0])
-    for a, b in zip(res[0][1], res[1][1]):
-        assert np.array_equal(a, b)
-    for a, b in zip(res[0][2], res[1][2]):
-        assert np.array_equal(a, b)
+    d0, d1 = res[0][1], res[1][1]               # (boxes, scores, class ids, candidate indices, counts, n_candidates): rows beyond counts are unset
+    assert np.array_equal(d0[4], d1[4]) and np.array_equal(d0[5], d1[5])
+    for b in range(2):
+        n = int(d0[4][b])
+        for k in range(4):
+            assert np.array_equal(d0[k][b, :n], d1[k][b, :n]), (b, k)
+    (p0, n0, s0, _), (p1, n1, s1, _) = res[0][2], res[1][2]      # lane points: entries beyond npts are unset
+    assert np.array_equal(n0, n1) and np.array_equal(s0, s1)
+    for b in range(2):
+        for l in range(4):
+            assert np.array_equal(p0[b, l, :n0[b, l]], p1[b, l, :n1[b, l]]), (b, l)
     for name in res[0][3].dtype.names:
         assert np.array_equal(res[0][3][name], res[1][3][name]), name
 

@@ -497,7 +497,12 @@ def main():
     ap.add_argument("--depth", type=int, default=3, help="batches queued ahead of the tracker")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample (0 disables)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of the --impl reference arm")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("ADAS_B200_WATCHDOG", "1500")),
+                    help="seconds after which a stuck run dumps every thread's stack to stderr and exits non-zero (0 disables)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True, file=sys.stderr)      # a hang must end loudly, with evidence
     if args.impl == "reference":
         run_reference(args)
     else:

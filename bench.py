@@ -348,7 +348,7 @@ def run_b200(args):
             "tracks_alive": len(pipe.tracker.tracked_stracks),
             "gather": ({"per_step": True, "nccl_ranks": comm.info()[0], "all_gathers": comm.info()[1], "bytes_per_rank_per_step": int(rec.nbytes)} if comm is not None else None),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"bound": "tensor", "kernel": "conv_gemm_v3_kernel + conv_chain_v3_kernel (tcgen05 implicit-GEMM conv/FC, persistent, staged TMA-store epilogue; the chain variant runs a run of same-shape layers in one launch)", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_v3_kernel (tcgen05 implicit-GEMM conv/FC, persistent, warp-specialised, staged TMA-store epilogue)", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_detail": traffic_detail,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; GEMM launches timed alone, of measured)" if peaks else "fallback 1590 (of fallback)",
                          "launches_per_step": n_y + n_u, "avg_launch_us": round(1e3 * (ms_y + ms_u) / (n_y + n_u), 2),

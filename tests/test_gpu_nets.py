@@ -491,6 +491,9 @@ def test_frames_to_detections_lanes_tracks_vs_cpu_reference_path():
     assert exact >= 6 and n_det > 0 and n_tracks_cmp > 0 and n_lane_pts > 1000
 
 
+@pytest.mark.skipif(os.environ.get("ADAS_B200_TEST_CHAIN") != "1",
+                    reason="gemm_chain.cu is EXPERIMENTAL and off by default (ADAS_B200_CHAIN): bit-exact in every run of this test, but one bench "
+                           "process in ~6 hung on the device with chains enabled; run with ADAS_B200_TEST_CHAIN=1")
 @pytest.mark.parametrize("kind,kw,B", [("yolov8", dict(scale="l"), 4), ("ufldv2", dict(backbone="34"), 4), ("yolov5", dict(scale="n"), 2)])
 def test_chain_launches_equal_per_layer_launches(kind, kw, B):
     """gemm_chain.cu: runs of same-shape convs (C2f bottlenecks, ResNet stages) execute as ONE launch with tile-level completion counters

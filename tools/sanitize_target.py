@@ -36,7 +36,7 @@ for i, (B, cin, cout, H, W, k, s, act, res, tile) in enumerate(CASES):
     eng.read_buffer(out.buf, B)
     eng.close()
     print("conv case", i, "ok", flush=True)
-# chain launch: four 3x3 64->64 layers, every second one with a residual = the input of the layer before it (C2f bottleneck pattern)
+# chain launch (EXPERIMENTAL kernel, off by default in the engine): four 3x3 64->64 layers, every second one with a residual = the input of the layer before it (C2f bottleneck pattern)
 os.environ["ADAS_B200_CHAIN"] = "1"
 pb = plan.PlanBuilder(plan.MODEL_YOLOV5, 3, 24, 24)
 x0 = pb.new_padded(24, 24, 64)

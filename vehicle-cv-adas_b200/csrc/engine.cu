@@ -57,8 +57,10 @@ struct adas_engine {
     int max_batch = 1;
     int conv_impl = 0;
     bool use_graph = true;
-    int use_chain = 2;            // ADAS_B200_CHAIN: 0 = one launch per layer, 1 = chain every eligible run, default 2 = chain a run only where the
-                                  // chain launch (gemm_chain.cu) timed faster than its per-layer launches when the program was built
+    int use_chain = 0;            // ADAS_B200_CHAIN: 0 (default) = one launch per layer; 2 = chain a run where the chain launch (gemm_chain.cu) timed
+                                  // faster than its per-layer launches when the program was built; 1 = chain every eligible run.  Off by default:
+                                  // one bench process in ~6 hung on the device with chains enabled (never with ADAS_B200_CHAIN=0, 16 runs) --
+                                  // root cause not found, see DESIGN.md section 4.2
     bool autotune = true;         // ADAS_B200_AUTOTUNE=0: modelled tile choice only
     cudaStream_t stream = nullptr;
     PlanHeader hdr;
@@ -758,7 +760,7 @@ int adas_engine_create(const char* plan_path, int device, int max_batch, int con
     const char* ng = getenv("ADAS_B200_NO_GRAPH");
     e->use_graph = !(ng && ng[0] == '1');
     const char* ch = getenv("ADAS_B200_CHAIN");
-    e->use_chain = !ch ? 2 : ch[0] == '0' ? 0 : ch[0] == '1' ? 1 : 2;
+    e->use_chain = !ch ? 0 : ch[0] == '0' ? 0 : ch[0] == '1' ? 1 : 2;
     const char* at = getenv("ADAS_B200_AUTOTUNE");
     e->autotune = !(at && at[0] == '0');
     bool ok = fread(&e->hdr, sizeof(PlanHeader), 1, f) == 1 && memcmp(e->hdr.magic, kPlanMagic, 8) == 0 && e->hdr.version == kPlanVersion;

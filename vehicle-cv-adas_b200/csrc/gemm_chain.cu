@@ -103,6 +103,16 @@ conv_chain_v3_kernel(const GemmV3 g, const ChainLayer* __restrict__ layers, int 
         asm volatile("griddepcontrol.wait;" ::: "memory");          // the previous kernel (incl. the previous launch of this chain) is complete
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
+    // The tensor maps of a chain live in GLOBAL memory (one set per layer), not in kernel parameters.  A chain object that is freed and
+    // another one allocated at the same address (the build-time comparison of candidate chains does exactly that) changes descriptors
+    // under the SMs' descriptor caches; the tensormap proxy fence makes every CTA re-read them.  (Hypothesis for the rare device hang
+    // of DESIGN.md 4.2: a stale weight-tile descriptor with a different box height delivers fewer bytes than the mbarrier expects.)
+    for (int i = threadIdx.x; i < n_layers * 4; i += blockDim.x) {
+        const ChainLayer* Lf = layers + (i >> 2);
+        const void* tm = (i & 3) == 0 ? (const void*)&Lf->tmA : (i & 3) == 1 ? (const void*)&Lf->tmB : (i & 3) == 2 ? (const void*)&Lf->tmC : (const void*)&Lf->tmR;
+        asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+    }
+    __syncthreads();
     const uint32_t epoch = ld_acquire_u32(ctl + 2);                // counters of all earlier launches are already in `flags`
     const uint32_t flag_target = (epoch + 1u) * (uint32_t)g.n_tiles;
 
